@@ -1,0 +1,165 @@
+// Shared device/host helpers for the cglb_b200 sm_100a library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cglb_b200.h"
+
+namespace cglb {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: every extern "C" entry returns int, never throws
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define CGLB_CUDA_OK(expr)                                                                  \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            cglb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return CGLB_ERR_CUDA;                                                           \
+        }                                                                                   \
+    } while (0)
+
+#define CGLB_CHECK_ARG(cond, msg)                                                           \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            cglb::set_error("invalid argument: %s (%s:%d)", msg, __FILE__, __LINE__);       \
+            return CGLB_ERR_ARG;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define CGLB_LAUNCH_OK()                                                                    \
+    do {                                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess) {                                                            \
+            cglb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return CGLB_ERR_CUDA;                                                           \
+        }                                                                                   \
+    } while (0)
+
+// Context: one per (device, stream user).  Owns small workspaces so that the entry points can stay
+// allocation-free on the hot path.
+struct Context {
+    int device;
+    int num_sms;
+    // work-stealing counters for the persistent kernels (one int per launch slot)
+    int* counters;        // [16]
+    // padded copies of the vector operands of the sweeps
+    double* vpad;         // [vpad_cap]
+    double* upad;         // [vpad_cap]
+    double* rsum;         // [vpad_cap]  row-sum scratch of the backward sweep
+    long vpad_cap;
+    double* scratch;      // generic scratch (partials of reductions)
+    long scratch_cap;
+    double* exp_table;    // 64 doubles 2^(j/64), staged into shared memory by the sweep kernels
+    unsigned long long launches;   // number of kernels this context launched (bench.py gpu_launches)
+};
+
+int ensure_vpad(Context* ctx, long n_pad);
+int ensure_scratch(Context* ctx, long n_doubles);
+
+// ---------------------------------------------------------------------------------------------
+// packed input layout (see DESIGN.md "data layout")
+//   row i of a packed array = DP doubles: scaled+centred coordinates a_0..a_{d-1}, zero padding,
+//   and the squared norm |a|^2 in the LAST slot.  DP = d+1 rounded up to even so that a row is a
+//   multiple of 16 bytes (TMA bulk copies and LDS.128 broadcasts need that).
+//   Rows are padded to a multiple of CGLB_ROW_PAD with zeros.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int packed_width(int d) { return (d + 2) & ~1; }
+__host__ __device__ inline long padded_rows(long n) { return (n + CGLB_ROW_PAD - 1) / CGLB_ROW_PAD * CGLB_ROW_PAD; }
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + TMA bulk copy wrappers (cp.async.bulk -> SASS UBLKCP)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0).
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 math tuned for the sweeps (DESIGN.md "kernel arithmetic"): the libm sqrt+exp pair costs
+// ~29 FP64 issue slots; these cost 5 + 9.
+// ---------------------------------------------------------------------------------------------
+
+// clamp a (possibly slightly negative, from the expanded-form cancellation) squared distance into
+// [2^-1000, 2^60] using integer min/max on the high word -- zero FP64-pipe cost.
+__device__ __forceinline__ double clamp_sq(double q) {
+    int hi = __double2hiint(q);
+    hi = max(hi, 0x01700000);   // ~2^-1000 ; negative doubles have hi < 0 as int
+    hi = min(hi, 0x43B00000);   // 2^60
+    return __hiloint2double(hi, __double2loint(q));
+}
+
+// sqrt(q) for q in [2^-1000, 2^60]: MUFU.RSQ64H seed (rel err 2^-20, measured) + one third-order
+// correction: s = g(1 + e/2 + 3e^2/8), e = 1 - q y^2  -> rel err ~ (5/16) e^3 < 1e-18.  5 FP64 slots.
+__device__ __forceinline__ double fast_sqrt(double q) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+    double g = q * y;
+    double e = fma(-g, y, 1.0);
+    double p = fma(e, 0.375, 0.5);
+    double t = e * p;
+    return fma(g, t, g);
+}
+
+// exp(-s) for s >= 0 (s <= 2^30): n = rint(-s*64/ln2), r = -s - n ln2/64 (|r| <= ln2/128),
+// e^r by a degree-5 polynomial, 2^(n/64) from a 64-entry table in shared memory and an exponent-field
+// add.  9 FP64 slots + 1 LDS + integer work.  Results below 2^-1000 are not meaningful (treated as 0
+// by every consumer: they are multiplied into sums of O(1) terms).
+__device__ __forceinline__ double fast_exp_neg(double s, const double* __restrict__ tab /* shared */) {
+    const double MAGIC = 6755399441055744.0;              // 1.5 * 2^52
+    const double C = 92.332482616893656820;                // 64 / ln 2
+    const double L = 1.0830424696249145255e-02;            // ln 2 / 64
+    double t = fma(s, -C, MAGIC);
+    int n = __double2loint(t);
+    double nf = t - MAGIC;
+    double r = fma(nf, -L, -s);
+    double p = fma(r, 8.3333333333333332177e-03, 4.1666666666666664354e-02);
+    p = fma(p, r, 1.6666666666666665741e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    double T = tab[n & 63];
+    int m = max(n >> 6, -1000);
+    double Tr = T * r;
+    double res = fma(Tr, p, T);
+    return __hiloint2double(__double2hiint(res) + (m << 20), __double2loint(res));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace cglb

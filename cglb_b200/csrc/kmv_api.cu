@@ -1,0 +1,195 @@
+// extern "C" entry points of the matrix-free sweeps (K1, K2) + input packing.
+#include "kmv_impl.cuh"
+
+namespace cglb {
+
+__global__ void pack_inputs_kernel(int kind, const double* __restrict__ x, long n, long n_pad, int d, int dp,
+                                   const double* __restrict__ ls, const double* __restrict__ shift,
+                                   double* __restrict__ xp) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    double* o = xp + i * dp;
+    if (i >= n) {
+        for (int k = 0; k < dp; ++k) o[k] = 0.0;
+        return;
+    }
+    const double c = (kind == CGLB_MATERN32) ? 1.7320508075688772935 : 0.70710678118654752440;
+    double nrm = 0.0;
+    for (int k = 0; k < d; ++k) {
+        double a = c * (x[i * d + k] - (shift ? shift[k] : 0.0)) / ls[k];
+        o[k] = a;
+        nrm = fma(a, a, nrm);
+    }
+    for (int k = d; k < dp - 1; ++k) o[k] = 0.0;
+    o[dp - 1] = nrm;
+}
+
+// vpad = [v, 0...]; y = diag * v (or 0)
+__global__ void kmv_prologue_kernel(const double* __restrict__ v, long n, long n_pad, double* __restrict__ vpad,
+                                    double* __restrict__ y, long ny, double diag) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) vpad[i] = (i < n) ? v[i] : 0.0;
+    if (y != nullptr && i < ny) y[i] = (i < n) ? diag * v[i] : 0.0;
+}
+
+__global__ void bwd_prologue_kernel(const double* __restrict__ u, const double* __restrict__ w, long n, long n_pad,
+                                    double* __restrict__ upad, double* __restrict__ wpad, double* __restrict__ rsum) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) {
+        upad[i] = (i < n) ? u[i] : 0.0;
+        wpad[i] = (i < n) ? w[i] : 0.0;
+        rsum[i] = 0.0;
+    }
+}
+
+// out[q] += (variance*cfac/ls_q) * ( sum_i a_iq^2 R_i + gq[q] ) ; out[d] += gvar      (single CTA per q chunk)
+__global__ void bwd_epilogue_kernel(const double* __restrict__ xp, long n, int d, int dp, const double* __restrict__ rsum,
+                                    const double* __restrict__ gtmp, const double* __restrict__ ls, double variance,
+                                    double cfac, double* __restrict__ out, int add_sweep_terms) {
+    // grid: d blocks (one per lengthscale) ; block 256 threads, deterministic tree reduction
+    const int q = blockIdx.x;
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) {
+        double a = xp[i * dp + q];
+        s = fma(a * a, rsum[i], s);
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double tot = sh[0] + (add_sweep_terms ? gtmp[q] : 0.0);
+        out[q] += variance * cfac / ls[q] * tot;
+        if (q == 0 && add_sweep_terms) out[d] += gtmp[d];
+    }
+}
+
+
+// CGLB_KMV_DIMS_LIST = "X(1) X(2) ..." : the dimensions this build instantiates (build.py passes it)
+#ifndef CGLB_KMV_DIMS_LIST
+#define CGLB_KMV_DIMS_LIST X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#endif
+#define X(DD) int sweep_d##DD(Context*, int, int, const SweepArgs&, cudaStream_t);
+CGLB_KMV_DIMS_LIST
+#undef X
+
+sweep_fn get_sweep_fn(int d) {
+    switch (d) {
+#define X(DD) \
+    case DD:  \
+        return sweep_d##DD;
+        CGLB_KMV_DIMS_LIST
+#undef X
+        default:
+            return nullptr;
+    }
+}
+
+static int dispatch(Context* ctx, int kind, int d, int mode, const SweepArgs& a, cudaStream_t st) {
+    sweep_fn f = get_sweep_fn(d);
+    if (!f) {
+        set_error("kernel sweep: d=%d has no register-resident instantiation in this build", d);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    return f(ctx, kind, mode, a, st);
+}
+
+}  // namespace cglb
+
+using namespace cglb;
+
+extern "C" int cglb_packed_width(int d) { return packed_width(d); }
+extern "C" long cglb_padded_rows(long n) { return padded_rows(n); }
+
+extern "C" int cglb_pack_inputs(cglb_context* c, int kind, const double* x, long n, int d, const double* lengthscale,
+                                const double* shift, double* xp, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && x && lengthscale && xp, "null pointer");
+    CGLB_CHECK_ARG(n >= 0 && d >= 1, "n >= 0, d >= 1");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    long n_pad = padded_rows(n);
+    if (n_pad == 0) return CGLB_OK;
+    pack_inputs_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, x, n, n_pad, d, packed_width(d),
+                                                                                         lengthscale, shift, xp);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+extern "C" int cglb_kmv_sym(cglb_context* c, int kind, const double* xp, long n, int d, const double* v, double* y,
+                            double variance, double diag, int part, int nparts, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && xp && v && y, "null pointer");
+    CGLB_CHECK_ARG(nparts >= 1 && part >= 0 && part < nparts, "part/nparts");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    if (n == 0) return CGLB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long n_pad = padded_rows(n);
+    // the symmetric sweep reads rows in blocks of up to 1024: pad the vector accordingly
+    long v_pad = (n + 1023) / 1024 * 1024;
+    int rc = ensure_vpad(ctx, v_pad);
+    if (rc) return rc;
+    (void)n_pad;
+    kmv_prologue_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(v, n, v_pad, ctx->vpad, y, n, part == 0 ? diag : 0.0);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    SweepArgs a{};
+    a.xp_rows = xp; a.xp_cols = xp; a.vcol = ctx->vpad; a.ucol = nullptr; a.y = y; a.gout = nullptr;
+    a.nrows = n; a.ncols = n; a.exp_tab = ctx->exp_table; a.variance = variance; a.part = part; a.nparts = nparts;
+    return dispatch(ctx, kind, d, 0, a, st);
+}
+
+extern "C" int cglb_kmv_rect(cglb_context* c, int kind, const double* xp_rows, long nrows, const double* xp_cols,
+                             long ncols, int d, const double* v, double* y, double variance, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && xp_rows && xp_cols && v && y, "null pointer");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    if (nrows == 0) return CGLB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long v_pad = (ncols + 1023) / 1024 * 1024;
+    int rc = ensure_vpad(ctx, v_pad);
+    if (rc) return rc;
+    kmv_prologue_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(v, ncols, v_pad, ctx->vpad, nullptr, 0, 0.0);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    CGLB_CUDA_OK(cudaMemsetAsync(y, 0, sizeof(double) * nrows, st));
+    if (ncols == 0) return CGLB_OK;
+    SweepArgs a{};
+    a.xp_rows = xp_rows; a.xp_cols = xp_cols; a.vcol = ctx->vpad; a.y = y;
+    a.nrows = nrows; a.ncols = ncols; a.exp_tab = ctx->exp_table; a.variance = variance; a.part = 0; a.nparts = 1;
+    return dispatch(ctx, kind, d, 1, a, st);
+}
+
+extern "C" int cglb_kmv_bwd_sym(cglb_context* c, int kind, const double* xp, long n, int d, const double* u,
+                                const double* w, double variance, const double* lengthscale, double* out, int part,
+                                int nparts, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && xp && u && w && out && lengthscale, "null pointer");
+    CGLB_CHECK_ARG(nparts >= 1 && part >= 0 && part < nparts, "part/nparts");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    if (n == 0) return CGLB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long v_pad = (n + 1023) / 1024 * 1024;
+    int rc = ensure_vpad(ctx, v_pad);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, 64);
+    if (rc) return rc;
+    bwd_prologue_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(u, w, n, v_pad, ctx->upad, ctx->vpad, ctx->rsum);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    CGLB_CUDA_OK(cudaMemsetAsync(ctx->scratch, 0, sizeof(double) * 64, st));
+    SweepArgs a{};
+    a.xp_rows = xp; a.xp_cols = xp; a.vcol = ctx->vpad; a.ucol = ctx->upad; a.y = ctx->rsum; a.gout = ctx->scratch;
+    a.nrows = n; a.ncols = n; a.exp_tab = ctx->exp_table; a.variance = variance; a.part = part; a.nparts = nparts;
+    rc = dispatch(ctx, kind, d, 2, a, st);
+    if (rc) return rc;
+    // dk/dl_q = variance * e' * delta_q^2 / l_q with e' = e^-s (Matern32) or 2 e^-q (RBF)
+    const double cfac = (kind == CGLB_MATERN32) ? 1.0 : 2.0;
+    bwd_epilogue_kernel<<<d, 256, 0, st>>>(xp, n, d, packed_width(d), ctx->rsum, ctx->scratch, lengthscale, variance, cfac, out, 1);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}

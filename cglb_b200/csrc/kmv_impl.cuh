@@ -1,0 +1,556 @@
+// K1 / K2: matrix-free kernel-evaluate-and-matvec sweeps for sm_100a.
+//
+//   y = variance * K(X,X) v + diag * v          (cglb_kmv_sym, cglb_kmv_rect)
+//   d(u^T K w)/d{lengthscale, variance}          (cglb_kmv_bwd_sym)
+//
+// Replaces the KeOps Genred reductions behind `A @ p` (reference conjugate_gradient.py:57,66,72,
+// models.py:280) and their autograd (optimizer.py:97).  Design:
+//   * persistent CTAs (one per SM), 8 warps; lane 0 of warp 0 also drives the TMA ring two tiles ahead;
+//   * a work item is a (row block, column chunk) square of BI x BI kernel pairs; the symmetric sweep
+//     visits only chunks on or above the diagonal and uses every evaluated k_ij for y_i AND y_j;
+//   * each consumer thread keeps TI rows (scaled coordinates, -2a and |a|^2) in registers; column tiles
+//     of BJ packed rows + the matching slice of v arrive in shared memory through cp.async.bulk (TMA)
+//     on a 4-stage mbarrier ring and are read as warp-wide broadcasts;
+//   * squared distances in the expanded form |a|^2+|b|^2-2ab (d+1 DFMA-class slots instead of 2d),
+//     clamped in the integer pipe, sqrt/exp from common.cuh (5+9 slots);
+//   * column sums: transposing butterfly over groups of CG columns (9 DADD per 8 columns), then a
+//     cross-warp shared-memory reduction and one RED.ADD.F64 per column per tile.
+#pragma once
+#include "common.cuh"
+
+namespace cglb {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;             // every warp computes; warp 0 / lane 0 also drives TMA
+constexpr int kBJ = 64;                           // columns per pipeline stage
+constexpr int kStages = 4;
+constexpr int kPrefetch = 2;                      // tiles in flight ahead of the one being consumed
+constexpr int kCG = 8;                            // column group of the transposing reduction
+
+struct SweepArgs {
+    const double* xp_rows;   // packed rows   [rows_pad][DP]
+    const double* xp_cols;   // packed cols   [cols_pad][DP]
+    const double* vcol;      // padded column vector (v for fwd; w for bwd)   [cols_pad]
+    const double* ucol;      // bwd only: u on the column side                [cols_pad]
+    double* y;               // fwd: output (atomically accumulated); bwd: R row sums
+    double* gout;            // bwd: [D+1] accumulators (-2 X_q ..., variance sum)
+    long nrows, ncols;       // valid counts
+    long nb_rows, nb_cols;   // number of BI blocks
+    long nitems;             // total work items (global, before the part split)
+    const double* exp_tab;   // 64 doubles 2^(j/64) in global memory
+    double variance;
+    int part, nparts;
+};
+
+template <int CLAMP_HI>
+__device__ __forceinline__ double clamp_sq_t(double q) {
+    int hi = __double2hiint(q);
+    hi = max(hi, 0x01700000);   // 2^-1000 (negative q -> hi < 0 as a signed int)
+    hi = min(hi, CLAMP_HI);
+    return __hiloint2double(hi, __double2loint(q));
+}
+
+// kappa(q): Matern32 -> (1+s) e^-s with s = sqrt(q) (inputs pre-scaled by sqrt3/l);  RBF -> e^-q
+template <int KIND>
+__device__ __forceinline__ double kappa(double q, const double* tab) {
+    if (KIND == CGLB_MATERN32) {
+        q = clamp_sq_t<0x42F00000>(q);   // s <= 2^24 keeps rint(-s*64/ln2) inside int32
+        double s = fast_sqrt(q);
+        double e = fast_exp_neg(s, tab);
+        return fma(s, e, e);
+    } else {
+        q = clamp_sq_t<0x41700000>(q);
+        return fast_exp_neg(q, tab);
+    }
+}
+
+// kappa and the lengthscale-derivative weight e' (Matern32: e^-s; RBF: e^-q, factor 2 applied by host)
+template <int KIND>
+__device__ __forceinline__ void kappa_and_dweight(double q, const double* tab, double& kap, double& ew) {
+    if (KIND == CGLB_MATERN32) {
+        q = clamp_sq_t<0x42F00000>(q);
+        double s = fast_sqrt(q);
+        ew = fast_exp_neg(s, tab);
+        kap = fma(s, ew, ew);
+    } else {
+        q = clamp_sq_t<0x41700000>(q);
+        ew = fast_exp_neg(q, tab);
+        kap = ew;
+    }
+}
+
+// Transposing butterfly: every lane holds CG partial column sums; on return lanes with
+// (lane & (32/CG - 1)) == 0 hold in c[0] the warp-wide sum of column `reduced_col(lane)`.
+template <int CG>
+__device__ __forceinline__ void col_reduce(double (&c)[CG], int lane) {
+    int cnt = CG;
+    int off = 16;
+#pragma unroll
+    for (; cnt > 1; cnt >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int h = 0; h < cnt / 2; ++h) {
+            double send = up ? c[h] : c[h + cnt / 2];
+            double keep = up ? c[h + cnt / 2] : c[h];
+            c[h] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+#pragma unroll
+    for (; off > 0; off >>= 1) c[0] += __shfl_xor_sync(0xffffffffu, c[0], off);
+}
+template <int CG>
+__device__ __forceinline__ int reduced_col(int lane) {
+    int col = 0, cnt = CG, off = 16;
+    for (; cnt > 1; cnt >>= 1, off >>= 1) col = col * 2 + ((lane & off) ? 1 : 0);
+    return col;
+}
+
+__device__ __forceinline__ void item_to_blocks_sym(long t, long& I, long& C) {
+    // t = C(C+1)/2 + I, I <= C
+    long c = (long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (c * (c + 1) / 2 > t) --c;
+    while ((c + 1) * (c + 2) / 2 <= t) ++c;
+    C = c;
+    I = t - c * (c + 1) / 2;
+}
+
+template <int D>
+struct SmemLayout {
+    static constexpr int DP = (D + 2) & ~1;
+};
+
+// Position in the static (round-robin over CTAs) stream of work items and of their column tiles.
+// The TMA-issuing lane and the consumers each walk their own cursor over the same sequence.
+template <int BI, bool SYM>
+struct Cursor {
+    long tau;       // local item counter: global item t = tau * nparts + part
+    long I, C;      // row block, column chunk
+    long c0;        // first column of the chunk
+    int tile, ntiles;
+    bool valid;
+    __device__ __forceinline__ void load_item(const SweepArgs& a) {
+        const long t = tau * a.nparts + a.part;
+        valid = t < a.nitems;
+        if (!valid) return;
+        if (SYM) item_to_blocks_sym(t, I, C);
+        else { I = t / a.nb_cols; C = t % a.nb_cols; }
+        c0 = C * BI;
+        long cend = c0 + BI;
+        if (cend > a.ncols) cend = a.ncols;
+        ntiles = (int)((cend - c0 + kBJ - 1) / kBJ);
+        tile = 0;
+    }
+    __device__ __forceinline__ void start(const SweepArgs& a) { tau = blockIdx.x; load_item(a); }
+    __device__ __forceinline__ void next_item(const SweepArgs& a) { tau += gridDim.x; load_item(a); }
+    __device__ __forceinline__ void next_tile(const SweepArgs& a) { if (++tile == ntiles) next_item(a); }
+};
+
+// mbarrier ring shared by the forward and backward sweeps.  NVEC = vectors staged per tile (1: v; 2: w,u)
+template <int D, int NVEC>
+struct TileRing {
+    static constexpr int DP = SmemLayout<D>::DP;
+    double* s_x;          // [kStages][kBJ*DP]
+    double* s_v;          // [kStages][NVEC][kBJ]
+    uint64_t* s_full;     // [kStages]
+    uint64_t* s_empty;    // [kStages]
+    int pstage; uint32_t pphase;     // producer side
+    int stage;  uint32_t phase;      // consumer side
+
+    __device__ __forceinline__ void init_barriers() {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kWarps);
+        }
+        mbar_fence_init();
+    }
+    template <class CursorT>
+    __device__ __forceinline__ void produce(CursorT& pc, const SweepArgs& a) {   // one lane only
+        if (!pc.valid) return;
+        mbar_wait(&s_empty[pstage], pphase ^ 1);
+        const long j0 = pc.c0 + (long)pc.tile * kBJ;
+        mbar_expect_tx(&s_full[pstage], (uint32_t)((kBJ * DP + NVEC * kBJ) * sizeof(double)));
+        tma_load_1d(s_x + pstage * kBJ * DP, a.xp_cols + j0 * DP, kBJ * DP * sizeof(double), &s_full[pstage]);
+        tma_load_1d(s_v + pstage * NVEC * kBJ, a.vcol + j0, kBJ * sizeof(double), &s_full[pstage]);
+        if (NVEC == 2) tma_load_1d(s_v + pstage * NVEC * kBJ + kBJ, a.ucol + j0, kBJ * sizeof(double), &s_full[pstage]);
+        if (++pstage == kStages) { pstage = 0; pphase ^= 1; }
+        pc.next_tile(a);
+    }
+    __device__ __forceinline__ void consumer_wait() { mbar_wait(&s_full[stage], phase); }
+    __device__ __forceinline__ void consumer_release(int lane) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+};
+
+template <int D, int DP, int TI>
+__device__ __forceinline__ void load_rows(const double* __restrict__ xp, long r0, long nrows, int tid,
+                                          double (&a2)[TI][D], double (&na)[TI], bool (&live)[TI]) {
+#pragma unroll
+    for (int ti = 0; ti < TI; ++ti) {
+        const long row = r0 + ti * kThreads + tid;
+        live[ti] = row < nrows;
+        const double2* src = reinterpret_cast<const double2*>(xp + (live[ti] ? row : 0) * DP);
+        double tmp[DP];
+#pragma unroll
+        for (int h = 0; h < DP / 2; ++h) {
+            double2 p = __ldg(src + h);
+            tmp[2 * h] = live[ti] ? p.x : 0.0;
+            tmp[2 * h + 1] = live[ti] ? p.y : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) a2[ti][k] = -2.0 * tmp[k];
+        na[ti] = tmp[DP - 1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward sweep
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int D, int TI, bool SYM>
+__global__ void __launch_bounds__(kThreads, 1) kmv_sweep_kernel(const SweepArgs args) {
+    constexpr int DP = SmemLayout<D>::DP;
+    constexpr int BI = kThreads * TI;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileRing<D, 1> ring;
+    ring.s_x = reinterpret_cast<double*>(smem_raw);                       // [kStages][kBJ*DP]
+    ring.s_v = ring.s_x + kStages * kBJ * DP;                             // [kStages][kBJ]
+    double* s_col = ring.s_v + kStages * kBJ;                             // [2][kWarps][kBJ]
+    double* s_tab = s_col + 2 * kWarps * kBJ;                             // [64]
+    ring.s_full = reinterpret_cast<uint64_t*>(s_tab + 64);                // [kStages]
+    ring.s_empty = ring.s_full + kStages;
+    ring.pstage = ring.stage = 0;
+    ring.pphase = ring.phase = 0;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid < 64) s_tab[tid] = args.exp_tab[tid];
+    if (tid == 0) ring.init_barriers();
+    __syncthreads();
+
+    Cursor<BI, SYM> cc, pc;     // consumer / producer cursors
+    cc.start(args);
+    pc = cc;
+    if (tid == 0) {
+#pragma unroll 1
+        for (int i = 0; i < kPrefetch; ++i) ring.produce(pc, args);
+    }
+    int colbuf = 0;
+    const double var = args.variance;
+
+    while (cc.valid) {
+        const bool offdiag = SYM && (cc.I != cc.C);
+        const long r0 = cc.I * BI;
+        double a2[TI][D], na[TI], vi[TI], racc[TI];
+        bool live[TI];
+        load_rows<D, DP, TI>(args.xp_rows, r0, args.nrows, tid, a2, na, live);
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti) {
+            // SYM: rows and columns share the padded vector
+            vi[ti] = (SYM && live[ti]) ? __ldg(args.vcol + r0 + ti * kThreads + tid) : 0.0;
+            racc[ti] = 0.0;
+        }
+        const int ntiles = cc.ntiles;
+        const long c0 = cc.c0;
+#pragma unroll 1
+        for (int tile = 0; tile < ntiles; ++tile) {
+            if (tid == 0) ring.produce(pc, args);
+            __syncwarp();
+            ring.consumer_wait();
+            const double* sx = ring.s_x + ring.stage * kBJ * DP;
+            const double* sv = ring.s_v + ring.stage * kBJ;
+            double* scol = s_col + (colbuf * kWarps + warp) * kBJ;
+#pragma unroll 1
+            for (int jg = 0; jg < kBJ; jg += kCG) {
+                double c[kCG];
+#pragma unroll
+                for (int jj = 0; jj < kCG; ++jj) {
+                    const double2* bp = reinterpret_cast<const double2*>(sx + (jg + jj) * DP);
+                    double b[DP];
+#pragma unroll
+                    for (int h = 0; h < DP / 2; ++h) {
+                        double2 p = bp[h];
+                        b[2 * h] = p.x;
+                        b[2 * h + 1] = p.y;
+                    }
+                    const double nb = b[DP - 1];
+                    const double vj = sv[jg + jj];
+                    double cs = 0.0;
+#pragma unroll
+                    for (int ti = 0; ti < TI; ++ti) {
+                        double q = na[ti] + nb;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) q = fma(a2[ti][k], b[k], q);
+                        const double kk = kappa<KIND>(q, s_tab);
+                        racc[ti] = fma(kk, vj, racc[ti]);
+                        if (SYM) cs = fma(kk, vi[ti], cs);
+                    }
+                    c[jj] = cs;
+                }
+                if (offdiag) {
+                    col_reduce<kCG>(c, lane);
+                    if ((lane & (32 / kCG - 1)) == 0) scol[jg + reduced_col<kCG>(lane)] = c[0];
+                }
+            }
+            ring.consumer_release(lane);
+
+            if (offdiag) {
+                // cross-warp reduction of the column sums of this tile, one RED per column
+                __syncthreads();
+                if (tid < kBJ) {
+                    const long j = c0 + (long)tile * kBJ + tid;
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) s += s_col[(colbuf * kWarps + w) * kBJ + tid];
+                    if (j < args.ncols) atomicAdd(args.y + j, var * s);
+                }
+                colbuf ^= 1;
+            }
+        }
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti)
+            if (live[ti]) atomicAdd(args.y + r0 + ti * kThreads + tid, var * racc[ti]);
+        cc.next_item(args);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward sweep (symmetric only):  see DESIGN.md section 3.3
+//   per unordered pair: omega = u_i w_j + w_i u_j, c = e' * omega
+//   R_i += c, R_j += c                      (args.y = R, atomics)
+//   gq[k] += b_jk * sum_ti c * (-2 a_ik)    (= -2 X_k, thread-private, reduced at kernel end)
+//   gvar  += kappa * omega
+// diagonal items visit ordered pairs with u_i,w_i halved and double their row sums at the end.
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int D, int TI>
+__global__ void __launch_bounds__(kThreads, 1) kmv_bwd_kernel(const SweepArgs args) {
+    constexpr int DP = SmemLayout<D>::DP;
+    constexpr int BI = kThreads * TI;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileRing<D, 2> ring;
+    ring.s_x = reinterpret_cast<double*>(smem_raw);                       // [kStages][kBJ*DP]
+    ring.s_v = ring.s_x + kStages * kBJ * DP;                             // [kStages][2][kBJ]  (w, u)
+    double* s_col = ring.s_v + kStages * 2 * kBJ;                         // [2][kWarps][kBJ]
+    double* s_tab = s_col + 2 * kWarps * kBJ;                             // [64]
+    double* s_red = s_tab + 64;                                           // [kWarps][D+2]
+    ring.s_full = reinterpret_cast<uint64_t*>(s_red + kWarps * (D + 2));
+    ring.s_empty = ring.s_full + kStages;
+    ring.pstage = ring.stage = 0;
+    ring.pphase = ring.phase = 0;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid < 64) s_tab[tid] = args.exp_tab[tid];
+    if (tid == 0) ring.init_barriers();
+    __syncthreads();
+
+    Cursor<BI, true> cc, pc;
+    cc.start(args);
+    pc = cc;
+    if (tid == 0) {
+#pragma unroll 1
+        for (int i = 0; i < kPrefetch; ++i) ring.produce(pc, args);
+    }
+    int colbuf = 0;
+    double gq[D], gvar = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) gq[k] = 0.0;
+
+    while (cc.valid) {
+        const bool offdiag = (cc.I != cc.C);
+        const double half = offdiag ? 1.0 : 0.5;
+        const long r0 = cc.I * BI;
+        double a2[TI][D], na[TI], ui[TI], wi[TI], racc[TI];
+        bool live[TI];
+        load_rows<D, DP, TI>(args.xp_rows, r0, args.nrows, tid, a2, na, live);
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti) {
+            const long row = r0 + ti * kThreads + tid;
+            ui[ti] = live[ti] ? half * __ldg(args.ucol + row) : 0.0;
+            wi[ti] = live[ti] ? half * __ldg(args.vcol + row) : 0.0;
+            racc[ti] = 0.0;
+        }
+        const int ntiles = cc.ntiles;
+        const long c0 = cc.c0;
+#pragma unroll 1
+        for (int tile = 0; tile < ntiles; ++tile) {
+            if (tid == 0) ring.produce(pc, args);
+            __syncwarp();
+            ring.consumer_wait();
+            const double* sx = ring.s_x + ring.stage * kBJ * DP;
+            const double* sw = ring.s_v + ring.stage * 2 * kBJ;
+            const double* su = sw + kBJ;
+            double* scol = s_col + (colbuf * kWarps + warp) * kBJ;
+#pragma unroll 1
+            for (int jg = 0; jg < kBJ; jg += kCG) {
+                double c[kCG];
+#pragma unroll
+                for (int jj = 0; jj < kCG; ++jj) {
+                    const double2* bp = reinterpret_cast<const double2*>(sx + (jg + jj) * DP);
+                    double b[DP];
+#pragma unroll
+                    for (int h = 0; h < DP / 2; ++h) {
+                        double2 p = bp[h];
+                        b[2 * h] = p.x;
+                        b[2 * h + 1] = p.y;
+                    }
+                    const double nb = b[DP - 1];
+                    const double wj = sw[jg + jj], uj = su[jg + jj];
+                    double cs = 0.0;
+                    double wq[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) wq[k] = 0.0;
+#pragma unroll
+                    for (int ti = 0; ti < TI; ++ti) {
+                        double q = na[ti] + nb;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) q = fma(a2[ti][k], b[k], q);
+                        double kap, ew;
+                        kappa_and_dweight<KIND>(q, s_tab, kap, ew);
+                        const double om = fma(wi[ti], uj, ui[ti] * wj);
+                        const double cw = ew * om;
+                        gvar = fma(kap, om, gvar);
+                        racc[ti] += cw;
+                        cs += cw;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) wq[k] = fma(cw, a2[ti][k], wq[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < D; ++k) gq[k] = fma(b[k], wq[k], gq[k]);
+                    c[jj] = cs;
+                }
+                if (offdiag) {
+                    col_reduce<kCG>(c, lane);
+                    if ((lane & (32 / kCG - 1)) == 0) scol[jg + reduced_col<kCG>(lane)] = c[0];
+                }
+            }
+            ring.consumer_release(lane);
+
+            if (offdiag) {
+                __syncthreads();
+                if (tid < kBJ) {
+                    const long j = c0 + (long)tile * kBJ + tid;
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) s += s_col[(colbuf * kWarps + w) * kBJ + tid];
+                    if (j < args.ncols) atomicAdd(args.y + j, s);
+                }
+                colbuf ^= 1;
+            }
+        }
+        const double rscale = offdiag ? 1.0 : 2.0;
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti)
+            if (live[ti]) atomicAdd(args.y + r0 + ti * kThreads + tid, rscale * racc[ti]);
+        cc.next_item(args);
+    }
+
+    // block reduction of the thread-private accumulators -> one atomic per CTA per component
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double s = warp_sum(gq[k]);
+        if (lane == 0) s_red[warp * (D + 2) + k] = s;
+    }
+    {
+        double s = warp_sum(gvar);
+        if (lane == 0) s_red[warp * (D + 2) + D] = s;
+    }
+    __syncthreads();
+    if (tid <= D) {
+        double s = 0.0;
+        for (int w = 0; w < kWarps; ++w) s += s_red[w * (D + 2) + tid];
+        atomicAdd(args.gout + tid, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-dimension launchers (one translation unit per D, see kmv_inst.cu)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+static size_t fwd_smem_bytes() {
+    constexpr int DP = SmemLayout<D>::DP;
+    return (size_t)(kStages * kBJ * DP + kStages * kBJ + 2 * kWarps * kBJ + 64) * sizeof(double) +
+           2 * kStages * sizeof(uint64_t);
+}
+template <int D>
+static size_t bwd_smem_bytes() {
+    constexpr int DP = SmemLayout<D>::DP;
+    return (size_t)(kStages * kBJ * DP + kStages * 2 * kBJ + 2 * kWarps * kBJ + 64 + kWarps * (D + 2)) *
+               sizeof(double) +
+           2 * kStages * sizeof(uint64_t);
+}
+
+template <int KIND, int D, int TI, bool SYM>
+static int launch_fwd(Context* ctx, SweepArgs a, cudaStream_t st) {
+    constexpr long BI = kThreads * TI;
+    a.nb_rows = (a.nrows + BI - 1) / BI;
+    a.nb_cols = (a.ncols + BI - 1) / BI;
+    a.nitems = SYM ? a.nb_rows * (a.nb_rows + 1) / 2 : a.nb_rows * a.nb_cols;
+    auto kern = kmv_sweep_kernel<KIND, D, TI, SYM>;
+    size_t smem = fwd_smem_bytes<D>();
+    CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
+    if (my_items <= 0) return CGLB_OK;
+    int grid = (int)(my_items < ctx->num_sms ? my_items : ctx->num_sms);
+    kern<<<grid, kThreads, smem, st>>>(a);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+template <int KIND, int D, int TI>
+static int launch_bwd(Context* ctx, SweepArgs a, cudaStream_t st) {
+    constexpr long BI = kThreads * TI;
+    a.nb_rows = (a.nrows + BI - 1) / BI;
+    a.nb_cols = a.nb_rows;
+    a.nitems = a.nb_rows * (a.nb_rows + 1) / 2;
+    auto kern = kmv_bwd_kernel<KIND, D, TI>;
+    size_t smem = bwd_smem_bytes<D>();
+    CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
+    if (my_items <= 0) return CGLB_OK;
+    int grid = (int)(my_items < ctx->num_sms ? my_items : ctx->num_sms);
+    kern<<<grid, kThreads, smem, st>>>(a);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+// Rows per thread: big blocks amortise the column loads best; small problems need more items than SMs.
+static inline int pick_ti(const Context* ctx, long nrows, long ncols, bool sym, int nparts, int max_ti) {
+    for (int ti = max_ti; ti > 1; ti >>= 1) {
+        long bi = (long)kThreads * ti;
+        long nbr = (nrows + bi - 1) / bi, nbc = (ncols + bi - 1) / bi;
+        long items = (sym ? nbr * (nbr + 1) / 2 : nbr * nbc) / nparts;
+        if (items >= 12L * ctx->num_sms) return ti;
+    }
+    return 1;
+}
+
+template <int KIND, int D, bool SYM>
+static int run_fwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
+    constexpr int MAXTI = SYM ? ((D <= 12) ? 4 : 2) : 2;
+    const int ti = pick_ti(ctx, a.nrows, a.ncols, SYM, a.nparts, MAXTI);
+    if constexpr (MAXTI == 4) {
+        if (ti == 4) return launch_fwd<KIND, D, 4, SYM>(ctx, a, st);
+    }
+    if (ti >= 2) return launch_fwd<KIND, D, 2, SYM>(ctx, a, st);
+    return launch_fwd<KIND, D, 1, SYM>(ctx, a, st);
+}
+
+template <int KIND, int D>
+static int run_bwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
+    constexpr int MAXTI = (D <= 12) ? 2 : 1;
+    const int ti = pick_ti(ctx, a.nrows, a.ncols, true, a.nparts, MAXTI);
+    if constexpr (MAXTI == 2) {
+        if (ti == 2) return launch_bwd<KIND, D, 2>(ctx, a, st);
+    }
+    return launch_bwd<KIND, D, 1>(ctx, a, st);
+}
+
+// dispatch table filled by the per-D translation units
+typedef int (*sweep_fn)(Context*, int kind, int mode /*0 sym fwd, 1 rect fwd, 2 sym bwd*/, const SweepArgs&, cudaStream_t);
+constexpr int kMaxRegisterD = 16;
+sweep_fn get_sweep_fn(int d);
+
+}  // namespace cglb

@@ -1,0 +1,27 @@
+// One translation unit per input dimension D (compiled with -DCGLB_KMV_D=<d>), so the 16 x 2 x 8
+// template instantiations of the sweeps build in parallel.
+#include "kmv_impl.cuh"
+
+#ifndef CGLB_KMV_D
+#error "compile with -DCGLB_KMV_D=<d>"
+#endif
+
+namespace cglb {
+
+#define CGLB_CAT2(a, b) a##b
+#define CGLB_CAT(a, b) CGLB_CAT2(a, b)
+
+int CGLB_CAT(sweep_d, CGLB_KMV_D)(Context* ctx, int kind, int mode, const SweepArgs& a, cudaStream_t st) {
+    constexpr int D = CGLB_KMV_D;
+    if (kind == CGLB_MATERN32) {
+        if (mode == 0) return run_fwd<CGLB_MATERN32, D, true>(ctx, a, st);
+        if (mode == 1) return run_fwd<CGLB_MATERN32, D, false>(ctx, a, st);
+        return run_bwd<CGLB_MATERN32, D>(ctx, a, st);
+    } else {
+        if (mode == 0) return run_fwd<CGLB_RBF, D, true>(ctx, a, st);
+        if (mode == 1) return run_fwd<CGLB_RBF, D, false>(ctx, a, st);
+        return run_bwd<CGLB_RBF, D>(ctx, a, st);
+    }
+}
+
+}  // namespace cglb
