@@ -1,0 +1,494 @@
+// K5 / K6: dense FP64 linear algebra for the Nystrom preconditioner and log-det terms, sm_100a.
+//
+//   cglb_gemm             C = alpha A op(B) + beta C           DMMA.8x8x4 tiles, cp.async 3-stage ring
+//   cglb_syrk             C = A A^T (split-K, lower tiles + mirror, RED.ADD.F64)
+//   cglb_potrf            blocked right-looking Cholesky (128-wide panels)
+//   cglb_tri_inverse      L^-1 through inverted diagonal blocks + GEMMs
+//   cglb_trsm_left_lower  B <- alpha L^-1 B, one GEMM per 128-row block against [ -D^-1 L | alpha D^-1 ]
+//
+// Replaces torch.cholesky / torch.triangular_solve / A @ A^T at reference models.py:202-210
+// (cuSOLVER dpotrf, cuBLAS dtrsm/dgemm).  FP64 has no tcgen05 form; mma.sync.m8n8k4.f64 (DMMA) measured
+// 37.1 TFLOP/s on this B200 vs 34.2 for plain DFMA (profiles/fp64_peaks_r01.json), so the contraction
+// runs on DMMA.
+#include "common.cuh"
+
+namespace cglb {
+
+constexpr int GM = 128, GN = 128, GK = 16;
+constexpr int GPITCH_K = GK + 4;     // As[m][k], Bs(NT)[n][k]: pitch 20 doubles -> conflict-free fragment loads
+constexpr int GPITCH_N = GN + 4;     // Bs(NN)[k][n]: pitch 132
+constexpr int GSTAGES = 3;
+constexpr int GTHREADS = 256;
+constexpr int NB = 128;              // block size of the blocked factorisations
+
+enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_SYRK = 2 };
+
+struct GemmArgs {
+    const double* A; long lda;
+    const double* B; long ldb;
+    double* C; long ldc;
+    long m, n, k;
+    long k_chunk;         // K range handled per blockIdx.z
+    double alpha, beta;
+    int lower_only;       // skip tiles strictly above the block diagonal
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <bool TRANSB>
+struct GemmSmem {
+    static constexpr int kA = GM * GPITCH_K;
+    static constexpr int kB = TRANSB ? GN * GPITCH_K : GK * GPITCH_N;
+    static constexpr size_t bytes = (size_t)GSTAGES * (kA + kB) * sizeof(double);
+};
+
+// C tile (bm, bn) of size 128x128; 8 warps as 2 (m) x 4 (n), warp tile 64x32 = 8x4 DMMA tiles.
+template <bool TRANSB, int EPI>
+__global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + GSTAGES * GemmSmem<TRANSB>::kA;
+
+    const int bm = blockIdx.y, bn = blockIdx.x;
+    if (p.lower_only && bn > bm) return;
+    const long m0 = (long)bm * GM, n0 = (long)bn * GN;
+    const long kbeg = (long)blockIdx.z * p.k_chunk;
+    long kend = kbeg + p.k_chunk;
+    if (kend > p.k) kend = p.k;
+    const int nkt = (int)((kend - kbeg + GK - 1) / GK);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+
+    auto load_tile = [&](int kt, int stage) {
+        const long k0 = kbeg + (long)kt * GK;
+        double* a = sA + stage * GemmSmem<TRANSB>::kA;
+        double* b = sB + stage * GemmSmem<TRANSB>::kB;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = tid + i * GTHREADS;        // 1024 chunks of 16 B
+            const int row = c >> 3, kc = (c & 7) * 2;
+            const long gr = m0 + row, gk = k0 + kc;
+            long rem = kend - gk;
+            int bytes = (gr < p.m && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
+            const double* src = bytes ? p.A + gr * p.lda + gk : p.A;
+            cp_async16(a + row * GPITCH_K + kc, src, bytes);
+        }
+        if (TRANSB) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = tid + i * GTHREADS;
+                const int row = c >> 3, kc = (c & 7) * 2;
+                const long gr = n0 + row, gk = k0 + kc;
+                long rem = kend - gk;
+                int bytes = (gr < p.n && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
+                const double* src = bytes ? p.B + gr * p.ldb + gk : p.B;
+                cp_async16(b + row * GPITCH_K + kc, src, bytes);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = tid + i * GTHREADS;
+                const int row = c >> 6, nc = (c & 63) * 2;
+                const long gk = k0 + row, gc = n0 + nc;
+                long rem = p.n - gc;
+                int bytes = (gk < kend && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
+                const double* src = bytes ? p.B + gk * p.ldb + gc : p.B;
+                cp_async16(b + row * GPITCH_N + nc, src, bytes);
+            }
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < GSTAGES - 1; ++s) {
+        if (s < nkt) load_tile(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nkt; ++kt) {
+        cp_async_wait<GSTAGES - 2>();
+        __syncthreads();
+        if (kt + GSTAGES - 1 < nkt) load_tile(kt + GSTAGES - 1, (kt + GSTAGES - 1) % GSTAGES);
+        cp_async_commit();
+        const double* a = sA + (kt % GSTAGES) * GemmSmem<TRANSB>::kA + (wm * 64 + g) * GPITCH_K + t;
+        const double* b = TRANSB ? sB + (kt % GSTAGES) * GemmSmem<TRANSB>::kB + (wn * 32 + g) * GPITCH_K + t
+                                 : sB + (kt % GSTAGES) * GemmSmem<TRANSB>::kB + t * GPITCH_N + wn * 32 + g;
+#pragma unroll
+        for (int k4 = 0; k4 < GK / 4; ++k4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = a[i * 8 * GPITCH_K + k4 * 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = TRANSB ? b[j * 8 * GPITCH_K + k4 * 4] : b[k4 * 4 * GPITCH_N + j * 8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: lane holds (row g, cols 2t, 2t+1) of every 8x8 tile
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long row = m0 + wm * 64 + i * 8 + g;
+        if (row >= p.m) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long col = n0 + wn * 32 + j * 8 + 2 * t;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long cc = col + e;
+                if (cc >= p.n) continue;
+                const double val = p.alpha * acc[i][j][e];
+                if (EPI == EPI_STORE) {
+                    double* dst = p.C + row * p.ldc + cc;
+                    *dst = (p.beta == 0.0) ? val : fma(p.beta, *dst, val);
+                } else if (EPI == EPI_ATOMIC) {
+                    atomicAdd(p.C + row * p.ldc + cc, val);
+                } else {
+                    atomicAdd(p.C + row * p.ldc + cc, val);
+                    if (bm != bn) atomicAdd(p.C + cc * p.ldc + row, val);
+                }
+            }
+        }
+    }
+}
+
+template <bool TRANSB, int EPI>
+static int launch_gemm(Context* ctx, const GemmArgs& p, int ksplit, cudaStream_t st) {
+    if (p.m <= 0 || p.n <= 0) return CGLB_OK;
+    auto kern = gemm_kernel<TRANSB, EPI>;
+    size_t smem = GemmSmem<TRANSB>::bytes;
+    CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((p.n + GN - 1) / GN), (unsigned)((p.m + GM - 1) / GM), (unsigned)ksplit);
+    if (grid.y > 65535 || grid.z > 65535) {
+        set_error("gemm: m=%ld too large for grid.y", p.m);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    kern<<<grid, GTHREADS, smem, st>>>(p);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+static int gemm_checked(Context* ctx, int transb, long m, long n, long k, double alpha, const double* a, long lda,
+                        const double* b, long ldb, double beta, double* c, long ldc, cudaStream_t st) {
+    CGLB_CHECK_ARG(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0), "gemm operands must be 16-byte aligned");
+    CGLB_CHECK_ARG(lda % 2 == 0 && ldb % 2 == 0, "gemm leading dimensions must be even");
+    GemmArgs p{a, lda, b, ldb, c, ldc, m, n, k, (k + GK - 1) / GK * GK, alpha, beta, 0};
+    if (p.k_chunk == 0) p.k_chunk = GK;
+    return transb ? launch_gemm<true, EPI_STORE>(ctx, p, 1, st) : launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagonal blocks: Cholesky and/or inverse of one NB x NB block per CTA, all in shared memory.
+// Layout: one (NB x (NB+1)) array; strictly-lower part = L, upper part incl. diagonal = (L^-1)^T,
+// L's diagonal (and its reciprocal) in separate vectors.
+// ---------------------------------------------------------------------------------------------
+constexpr int DP1 = NB + 1;
+
+// mode 0: factor the block (a <- L, upper zeroed) and write inv(L) to dinv; mode 1: block already
+// holds L (lower), only invert.  nb_actual = rows in this block (<= NB).  info: 1+block on failure.
+__global__ void __launch_bounds__(256, 1) diag_block_kernel(double* a, long lda, long m, long first_block,
+                                                            double* dinv_base, int mode, int* info) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* s = reinterpret_cast<double*>(smem_raw);      // [NB][DP1]
+    double* sd = s + NB * DP1;                            // diagonal of L
+    double* sr = sd + NB;                                 // reciprocal diagonal
+    __shared__ int s_fail;
+    const long blk = first_block + blockIdx.x;
+    const long r0 = blk * NB;
+    const int nb = (int)((m - r0) < NB ? (m - r0) : NB);
+    double* ablk = a + r0 * lda + r0;
+    double* dinv = dinv_base + blk * (long)NB * NB;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    if (tid == 0) s_fail = 0;
+    // load lower triangle (incl. diag); pad with identity
+    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+        const int i = idx / NB, j = idx % NB;
+        double v = 0.0;
+        if (i < nb && j < nb && j <= i) v = ablk[(long)i * lda + j];
+        if (i >= nb && i == j) v = 1.0;
+        s[i * DP1 + j] = v;
+    }
+    __syncthreads();
+    if (mode == 0) {
+        // right-looking unblocked Cholesky on the lower triangle
+        for (int j = 0; j < NB; ++j) {
+            if (tid == 0) {
+                double d = s[j * DP1 + j];
+                if (!(d > 0.0)) { s_fail = 1; d = 1.0; }
+                d = sqrt(d);
+                sd[j] = d;
+                sr[j] = 1.0 / d;
+            }
+            __syncthreads();
+            const double rinv = sr[j];
+            for (int i = j + 1 + tid; i < NB; i += blockDim.x) s[i * DP1 + j] *= rinv;
+            __syncthreads();
+            // trailing update: s[i][k] -= s[i][j] * s[k][j] for j < k <= i   (16 x 16 thread grid)
+            for (int i = j + 1 + ty; i < NB; i += 16) {
+                const double lij = s[i * DP1 + j];
+                for (int k = j + 1 + tx; k <= i; k += 16) s[i * DP1 + k] = fma(-lij, s[k * DP1 + j], s[i * DP1 + k]);
+            }
+            __syncthreads();
+        }
+        // write L back, zero the upper triangle of the block
+        for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
+            const int i = idx / nb, j = idx % nb;
+            double v = (j < i) ? s[i * DP1 + j] : (j == i ? sd[i] : 0.0);
+            ablk[(long)i * lda + j] = v;
+        }
+        if (tid == 0 && s_fail) atomicCAS(info, 0, (int)(blk + 1));
+    } else {
+        for (int i = tid; i < NB; i += blockDim.x) {
+            double d = s[i * DP1 + i];
+            sd[i] = d;
+            sr[i] = 1.0 / d;
+        }
+    }
+    __syncthreads();
+    // inverse X = L^-1 stored transposed in the upper triangle: XT[c][j] = X[j][c]  (c <= j).
+    // right-looking forward substitution on all columns at once; working RHS B starts as identity.
+    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+        const int c = idx / NB, j = idx % NB;
+        if (j >= c) s[c * DP1 + j] = (j == c) ? 1.0 : 0.0;     // (diag of L is in sd, safe to overwrite)
+    }
+    __syncthreads();
+    for (int j = 0; j < NB; ++j) {
+        // X[j][c] = B[j][c] / L[j][j] for c <= j
+        const double rinv = sr[j];
+        for (int c = tid; c <= j; c += blockDim.x) s[c * DP1 + j] *= rinv;
+        __syncthreads();
+        // B[i][c] -= L[i][j] * X[j][c] for i > j, c <= j
+        for (int c = ty; c <= j; c += 16) {
+            const double xjc = s[c * DP1 + j];
+            for (int i = j + 1 + tx; i < NB; i += 16) s[c * DP1 + i] = fma(-s[i * DP1 + j], xjc, s[c * DP1 + i]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+        const int i = idx / NB, c = idx % NB;
+        dinv[idx] = (c <= i) ? s[c * DP1 + i] : 0.0;
+    }
+}
+
+static size_t diag_smem_bytes() { return (size_t)(NB * DP1 + 2 * NB) * sizeof(double); }
+
+static int launch_diag(Context* ctx, double* a, long lda, long m, long first_block, long nblocks, double* dinv, int mode,
+                       int* info, cudaStream_t st) {
+    size_t smem = diag_smem_bytes();
+    CGLB_CUDA_OK(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    diag_block_kernel<<<(unsigned)nblocks, 256, smem, st>>>(a, lda, m, first_block, dinv, mode, info);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+__global__ void zero_upper_kernel(double* a, long m, long lda) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * m) return;
+    long i = idx / m, j = idx % m;
+    if (j > i) a[i * lda + j] = 0.0;
+}
+
+__global__ void set_zero_kernel(double* a, long rows, long cols, long ld) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    a[(idx / cols) * ld + idx % cols] = 0.0;
+}
+
+// copies diag inverse blocks (scaled) into the block diagonal of dst
+__global__ void place_diag_blocks_kernel(const double* dinv, double* dst, long m, long ldd, double scale) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long nblk = (m + NB - 1) / NB;
+    if (idx >= nblk * NB * NB) return;
+    long blk = idx / (NB * NB);
+    int i = (int)((idx / NB) % NB), j = (int)(idx % NB);
+    long r = blk * NB + i, c = blk * NB + j;
+    if (r < m && c < m) dst[r * ldd + c] = scale * dinv[idx];
+}
+
+// workspace layout inside ctx->scratch for the blocked algorithms
+struct DenseWs {
+    double* dinv;   // [nblk][NB][NB]
+    double* lhat;   // [m_pad][m_pad]
+    long m_pad;
+};
+static int get_dense_ws(Context* ctx, long m, DenseWs& ws) {
+    long nblk = (m + NB - 1) / NB;
+    ws.m_pad = nblk * NB;
+    long need = nblk * NB * NB + ws.m_pad * ws.m_pad + 64;
+    int rc = ensure_scratch(ctx, need + 64);
+    if (rc) return rc;
+    // first 64 doubles of scratch are reserved for the sweeps' scalar accumulators
+    ws.dinv = ctx->scratch + 64;
+    ws.lhat = ws.dinv + nblk * NB * NB;
+    return CGLB_OK;
+}
+
+// lhat[k, 0:k) = -dinv_k * l[k, 0:k)   for every block row k   (one small GEMM per block row)
+static int build_lhat(Context* ctx, const double* l, long m, long ldl, const DenseWs& ws, cudaStream_t st) {
+    long nblk = (m + NB - 1) / NB;
+    for (long k = 1; k < nblk; ++k) {
+        long rows = (m - k * NB) < NB ? (m - k * NB) : NB;
+        // A-operand: dinv_k (NB x NB, lda NB) restricted to `rows` rows; B-operand: l[k*NB.., 0:k*NB) (K = rows)
+        GemmArgs p{ws.dinv + k * NB * NB, NB, l + k * NB * ldl, ldl, ws.lhat + k * NB * ws.m_pad, ws.m_pad,
+                   rows, k * NB, rows, NB, -1.0, 0.0, 0};
+        int rc = launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
+        if (rc) return rc;
+    }
+    return CGLB_OK;
+}
+
+}  // namespace cglb
+
+using namespace cglb;
+
+extern "C" int cglb_gemm(cglb_context* c, int transb, long m, long n, long k, double alpha, const double* a, long lda,
+                         const double* b, long ldb, double beta, double* cc, long ldc, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && a && b && cc, "null pointer");
+    CGLB_CHECK_ARG(m >= 0 && n >= 0 && k >= 0, "negative dimension");
+    return gemm_checked(ctx, transb, m, n, k, alpha, a, lda, b, ldb, beta, cc, ldc, (cudaStream_t)stream);
+}
+
+extern "C" int cglb_syrk(cglb_context* c, const double* a, long m, long n, long lda, double* cm, long ldc, int accumulate,
+                         void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && a && cm, "null pointer");
+    CGLB_CHECK_ARG(((uintptr_t)a % 16 == 0) && lda % 2 == 0, "syrk operand alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m == 0) return CGLB_OK;
+    if (!accumulate) {
+        set_zero_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, st>>>(cm, m, m, ldc);
+        ctx->launches++;
+        CGLB_LAUNCH_OK();
+    }
+    if (n == 0) return CGLB_OK;
+    long tiles_m = (m + GM - 1) / GM;
+    long lower_tiles = tiles_m * (tiles_m + 1) / 2;
+    // enough CTAs for ~4 waves, but at least 512 columns of K per chunk
+    long want = (4L * ctx->num_sms + lower_tiles - 1) / lower_tiles;
+    long max_split = (n + 511) / 512;
+    long ksplit = want < max_split ? want : max_split;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > 65535) ksplit = 65535;
+    long chunk = ((n + ksplit - 1) / ksplit + GK - 1) / GK * GK;
+    ksplit = (n + chunk - 1) / chunk;
+    GemmArgs p{a, lda, a, lda, cm, ldc, m, m, n, chunk, 1.0, 0.0, 1};
+    return launch_gemm<true, EPI_SYRK>(ctx, p, (int)ksplit, st);
+}
+
+extern "C" int cglb_potrf(cglb_context* c, double* a, long m, long lda, int* info_dev, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && a && info_dev, "null pointer");
+    CGLB_CHECK_ARG(((uintptr_t)a % 16 == 0) && lda % 2 == 0, "potrf operand alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m == 0) return CGLB_OK;
+    DenseWs ws;
+    int rc = get_dense_ws(ctx, m, ws);
+    if (rc) return rc;
+    CGLB_CUDA_OK(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
+    long nblk = (m + NB - 1) / NB;
+    for (long k = 0; k < nblk; ++k) {
+        rc = launch_diag(ctx, a, lda, m, k, 1, ws.dinv, 0, info_dev, st);
+        if (rc) return rc;
+        long r1 = (k + 1) * NB;
+        if (r1 >= m) break;
+        long rows = m - r1;
+        // panel: a[r1:, kNB:r1) <- a[r1:, kNB:r1) * dinv_k^T      (NT, in place: a CTA owns its rows)
+        GemmArgs pp{a + r1 * lda + k * NB, lda, ws.dinv + k * NB * NB, NB, a + r1 * lda + k * NB, lda,
+                    rows, NB, NB, NB, 1.0, 0.0, 0};
+        rc = launch_gemm<true, EPI_STORE>(ctx, pp, 1, st);
+        if (rc) return rc;
+        // trailing: a[r1:, r1:) -= P P^T  (lower tiles only)
+        GemmArgs pt{a + r1 * lda + k * NB, lda, a + r1 * lda + k * NB, lda, a + r1 * lda + r1, lda,
+                    rows, rows, NB, NB, -1.0, 1.0, 1};
+        rc = launch_gemm<true, EPI_STORE>(ctx, pt, 1, st);
+        if (rc) return rc;
+    }
+    zero_upper_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, st>>>(a, m, lda);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+extern "C" int cglb_tri_inverse(cglb_context* c, const double* l, long m, long ldl, double* linv, long ldi, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && l && linv, "null pointer");
+    CGLB_CHECK_ARG(((uintptr_t)l % 16 == 0) && ((uintptr_t)linv % 16 == 0) && ldl % 2 == 0 && ldi % 2 == 0, "alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m == 0) return CGLB_OK;
+    DenseWs ws;
+    int rc = get_dense_ws(ctx, m, ws);
+    if (rc) return rc;
+    long nblk = (m + NB - 1) / NB;
+    rc = launch_diag(ctx, const_cast<double*>(l), ldl, m, 0, nblk, ws.dinv, 1, nullptr, st);
+    if (rc) return rc;
+    rc = build_lhat(ctx, l, m, ldl, ws, st);
+    if (rc) return rc;
+    set_zero_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, st>>>(linv, m, m, ldi);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    place_diag_blocks_kernel<<<(unsigned)((nblk * NB * NB + 255) / 256), 256, 0, st>>>(ws.dinv, linv, m, ldi, 1.0);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    // linv[k, 0:k) = lhat[k, 0:k) * linv[0:k, 0:k)
+    for (long k = 1; k < nblk; ++k) {
+        long rows = (m - k * NB) < NB ? (m - k * NB) : NB;
+        GemmArgs p{ws.lhat + k * NB * ws.m_pad, ws.m_pad, linv, ldi, linv + k * NB * ldi, ldi,
+                   rows, k * NB, k * NB, k * NB, 1.0, 0.0, 0};
+        rc = launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
+        if (rc) return rc;
+    }
+    return CGLB_OK;
+}
+
+extern "C" int cglb_trsm_left_lower(cglb_context* c, const double* l, long m, long ldl, double* b, long n, long ldb,
+                                    double alpha, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && l && b, "null pointer");
+    CGLB_CHECK_ARG(((uintptr_t)l % 16 == 0) && ((uintptr_t)b % 16 == 0) && ldl % 2 == 0 && ldb % 2 == 0, "alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m == 0 || n == 0) return CGLB_OK;
+    DenseWs ws;
+    int rc = get_dense_ws(ctx, m, ws);
+    if (rc) return rc;
+    long nblk = (m + NB - 1) / NB;
+    rc = launch_diag(ctx, const_cast<double*>(l), ldl, m, 0, nblk, ws.dinv, 1, nullptr, st);
+    if (rc) return rc;
+    rc = build_lhat(ctx, l, m, ldl, ws, st);
+    if (rc) return rc;
+    // block diagonal of lhat <- alpha * dinv_k :   X_k = [lhat_k | alpha dinv_k] [X_0..X_{k-1}; B_k]
+    place_diag_blocks_kernel<<<(unsigned)((nblk * NB * NB + 255) / 256), 256, 0, st>>>(ws.dinv, ws.lhat, ws.m_pad, ws.m_pad, alpha);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    for (long k = 0; k < nblk; ++k) {
+        long rows = (m - k * NB) < NB ? (m - k * NB) : NB;
+        long kk = k * NB + rows;
+        GemmArgs p{ws.lhat + k * NB * ws.m_pad, ws.m_pad, b, ldb, b + k * NB * ldb, ldb,
+                   rows, n, kk, (kk + GK - 1) / GK * GK, 1.0, 0.0, 0};
+        rc = launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
+        if (rc) return rc;
+    }
+    return CGLB_OK;
+}

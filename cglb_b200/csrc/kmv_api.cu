@@ -72,9 +72,23 @@ __global__ void bwd_epilogue_kernel(const double* __restrict__ xp, long n, int d
 #ifndef CGLB_KMV_DIMS_LIST
 #define CGLB_KMV_DIMS_LIST X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 #endif
-#define X(DD) int sweep_d##DD(Context*, int, int, const SweepArgs&, cudaStream_t);
+#define X(DD)                                                              \
+    int sweep_d##DD(Context*, int, int, const SweepArgs&, cudaStream_t);   \
+    int knm_d##DD(Context*, int, int, const KnmArgs&, cudaStream_t);
 CGLB_KMV_DIMS_LIST
 #undef X
+
+knm_fn get_knm_fn(int d) {
+    switch (d) {
+#define X(DD) \
+    case DD:  \
+        return knm_d##DD;
+        CGLB_KMV_DIMS_LIST
+#undef X
+        default:
+            return nullptr;
+    }
+}
 
 sweep_fn get_sweep_fn(int d) {
     switch (d) {
@@ -192,4 +206,41 @@ extern "C" int cglb_kmv_bwd_sym(cglb_context* c, int kind, const double* xp, lon
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;
+}
+
+extern "C" int cglb_knm_build(cglb_context* c, int kind, const double* zp, long m, const double* xp, long n, int d,
+                              double variance, double* out, long ld, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && zp && xp && out, "null pointer");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    CGLB_CHECK_ARG(ld >= n, "ld >= n");
+    knm_fn f = get_knm_fn(d);
+    if (!f) {
+        set_error("knm_build: d=%d has no instantiation in this build", d);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    KnmArgs a{};
+    a.zp = zp; a.m = m; a.xp = xp; a.ncols = n; a.out = out; a.ld = ld; a.exp_tab = ctx->exp_table; a.variance = variance;
+    return f(ctx, kind, 0, a, (cudaStream_t)stream);
+}
+
+extern "C" int cglb_knm_backward(cglb_context* c, int kind, const double* zp, long m, const double* xp, long ncols, int d,
+                                 double variance, const double* lengthscale, const double* t, long ldt, const double* wt,
+                                 const double* zvec, double* out_ls, double* out_var, double* out_z, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && zp && xp && lengthscale && out_ls && out_var, "null pointer");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    CGLB_CHECK_ARG((wt == nullptr) == (zvec == nullptr), "wt and zvec go together");
+    knm_fn f = get_knm_fn(d);
+    if (!f) {
+        set_error("knm_backward: d=%d has no instantiation in this build", d);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    KnmArgs a{};
+    a.zp = zp; a.m = m; a.xp = xp; a.ncols = ncols; a.exp_tab = ctx->exp_table; a.variance = variance;
+    a.t = t; a.ldt = ldt; a.wt = wt; a.zvec = zvec; a.lengthscale = lengthscale;
+    a.out_ls = out_ls; a.out_var = out_var; a.out_z = out_z;
+    a.cscale = (kind == CGLB_MATERN32) ? 1.7320508075688772935 : 0.70710678118654752440;
+    a.cfac = (kind == CGLB_MATERN32) ? 1.0 : 2.0;
+    return f(ctx, kind, 1, a, (cudaStream_t)stream);
 }

@@ -464,6 +464,172 @@ __global__ void __launch_bounds__(kThreads, 1) kmv_bwd_kernel(const SweepArgs ar
 }
 
 // ---------------------------------------------------------------------------------------------
+// K7: dense cross-covariance  out[m][i] = variance * kappa(z_m, x_i)      (thread = column i)
+// ---------------------------------------------------------------------------------------------
+struct KnmArgs {
+    const double* zp; long m;          // packed inducing points [m_pad][DP]
+    const double* xp; long ncols;      // packed inputs          [n_pad][DP]
+    double* out; long ld;              // build: M x ld output
+    const double* exp_tab;
+    double variance;
+    // backward only
+    const double* t; long ldt;         // dS/dKuf dense part (may be null)
+    const double* wt;                  // [m]   rank-one part: G_mi = t_mi + wt_m * zvec_i
+    const double* zvec;                // [ncols]
+    const double* lengthscale;         // [D]
+    double* out_ls;                    // [D]   accumulated
+    double* out_var;                   // [1]   accumulated
+    double* out_z;                     // [m][D] accumulated
+    double cscale;                     // sqrt3 (Matern32) or 1/sqrt2 (RBF): packed = cscale * (x - shift) / l
+    double cfac;                       // 1 (Matern32) or 2 (RBF)
+};
+
+constexpr int kKnmRows = 64;           // rows of Z per CTA (build)
+constexpr int kKnmBwdRows = 32;        // rows of Z per CTA (backward: per-warp partial slabs live in smem)
+
+template <int KIND, int D>
+__global__ void __launch_bounds__(256) knm_build_kernel(const KnmArgs args) {
+    constexpr int DP = SmemLayout<D>::DP;
+    __shared__ __align__(16) double s_z[kKnmRows * DP];
+    __shared__ double s_tab[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) s_tab[tid] = args.exp_tab[tid];
+    const long m0 = (long)blockIdx.y * kKnmRows;
+    const int mr = (int)((args.m - m0) < kKnmRows ? (args.m - m0) : kKnmRows);
+    for (int i = tid; i < mr * DP; i += blockDim.x) s_z[i] = args.zp[m0 * DP + i];
+    __syncthreads();
+    const long col = (long)blockIdx.x * blockDim.x + tid;
+    if (col >= args.ncols) return;
+    double a2[D], na;
+    {
+        const double2* src = reinterpret_cast<const double2*>(args.xp + col * DP);
+        double tmp[DP];
+#pragma unroll
+        for (int h = 0; h < DP / 2; ++h) {
+            double2 p = __ldg(src + h);
+            tmp[2 * h] = p.x;
+            tmp[2 * h + 1] = p.y;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) a2[k] = -2.0 * tmp[k];
+        na = tmp[DP - 1];
+    }
+#pragma unroll 4
+    for (int mm = 0; mm < mr; ++mm) {
+        const double* b = s_z + mm * DP;
+        double q = na + b[DP - 1];
+#pragma unroll
+        for (int k = 0; k < D; ++k) q = fma(a2[k], b[k], q);
+        args.out[(m0 + mm) * args.ld + col] = args.variance * kappa<KIND>(q, s_tab);
+    }
+}
+
+// backward of the cross-covariance: thread = column i, loops over a chunk of inducing points.
+template <int KIND, int D>
+__global__ void __launch_bounds__(256) knm_bwd_kernel(const KnmArgs args) {
+    constexpr int DP = SmemLayout<D>::DP;
+    constexpr int CGR = D <= 1 ? 1 : D <= 2 ? 2 : D <= 4 ? 4 : D <= 8 ? 8 : 16;
+    __shared__ __align__(16) double s_z[kKnmBwdRows * DP];
+    __shared__ double s_tab[64];
+    __shared__ double s_wt[kKnmBwdRows];
+    __shared__ double s_part[8][kKnmBwdRows][CGR];     // per-warp partial sums of g' * delta_k for every row
+    __shared__ double s_red[8][D + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 64) s_tab[tid] = args.exp_tab[tid];
+    const long m0 = (long)blockIdx.y * kKnmBwdRows;
+    const int mr = (int)((args.m - m0) < kKnmBwdRows ? (args.m - m0) : kKnmBwdRows);
+    for (int i = tid; i < mr * DP; i += blockDim.x) s_z[i] = args.zp[m0 * DP + i];
+    for (int i = tid; i < mr; i += blockDim.x) s_wt[i] = args.wt ? args.wt[m0 + i] : 0.0;
+    __syncthreads();
+    const long col = (long)blockIdx.x * blockDim.x + tid;
+    const bool live = col < args.ncols;
+    double x[D];
+    {
+        const double2* src = reinterpret_cast<const double2*>(args.xp + (live ? col : 0) * DP);
+        double tmp[DP];
+#pragma unroll
+        for (int h = 0; h < DP / 2; ++h) {
+            double2 p = __ldg(src + h);
+            tmp[2 * h] = p.x;
+            tmp[2 * h + 1] = p.y;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] = tmp[k];
+    }
+    const double zv = (live && args.zvec) ? args.zvec[col] : 0.0;
+    const double vc = args.variance * args.cfac;
+    double bl[D], bvar = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) bl[k] = 0.0;
+
+    for (int mm = 0; mm < mr; ++mm) {
+        const double* b = s_z + mm * DP;
+        double del[D], q = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            del[k] = b[k] - x[k];
+            q = fma(del[k], del[k], q);
+        }
+        double kap, ew;
+        kappa_and_dweight<KIND>(q, s_tab, kap, ew);
+        double G = s_wt[mm] * zv;
+        if (args.t && live) G += args.t[(m0 + mm) * args.ldt + col];
+        if (!live) G = 0.0;
+        bvar = fma(G, kap, bvar);
+        const double gp = G * ew * vc;
+        double c[CGR];
+#pragma unroll
+        for (int k = 0; k < CGR; ++k) c[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double tk = gp * del[k];
+            c[k] = tk;
+            bl[k] = fma(tk, del[k], bl[k]);
+        }
+        col_reduce<CGR>(c, lane);
+        if ((lane & (32 / CGR - 1)) == 0) s_part[warp][mm][reduced_col<CGR>(lane)] = c[0];
+    }
+    __syncthreads();
+    // out_z[m][k] += -(cscale / l_k) * sum_warps
+    for (int idx = tid; idx < mr * D; idx += blockDim.x) {
+        const int mm = idx / D, k = idx % D;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_part[w][mm][k];
+        if (args.out_z) atomicAdd(args.out_z + (m0 + mm) * D + k, -args.cscale / args.lengthscale[k] * s);
+    }
+    // lengthscale / variance sums: block reduce, one atomic per CTA per component
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double s = warp_sum(bl[k]);
+        if (lane == 0) s_red[warp][k] = s;
+    }
+    {
+        double s = warp_sum(bvar);
+        if (lane == 0) s_red[warp][D] = s;
+    }
+    __syncthreads();
+    if (tid <= D) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += s_red[w][tid];
+        if (tid < D) atomicAdd(args.out_ls + tid, s / args.lengthscale[tid]);
+        else atomicAdd(args.out_var, s);
+    }
+}
+
+template <int KIND, int D>
+static int run_knm(Context* ctx, int bwd, const KnmArgs& a, cudaStream_t st) {
+    if (a.m <= 0 || a.ncols <= 0) return CGLB_OK;
+    const int rows = bwd ? kKnmBwdRows : kKnmRows;
+    dim3 grid((unsigned)((a.ncols + 255) / 256), (unsigned)((a.m + rows - 1) / rows));
+    if (bwd) knm_bwd_kernel<KIND, D><<<grid, 256, 0, st>>>(a);
+    else knm_build_kernel<KIND, D><<<grid, 256, 0, st>>>(a);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-dimension launchers (one translation unit per D, see kmv_inst.cu)
 // ---------------------------------------------------------------------------------------------
 template <int D>
@@ -550,6 +716,8 @@ static int run_bwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
 
 // dispatch table filled by the per-D translation units
 typedef int (*sweep_fn)(Context*, int kind, int mode /*0 sym fwd, 1 rect fwd, 2 sym bwd*/, const SweepArgs&, cudaStream_t);
+typedef int (*knm_fn)(Context*, int kind, int bwd, const KnmArgs&, cudaStream_t);
+knm_fn get_knm_fn(int d);
 constexpr int kMaxRegisterD = 16;
 sweep_fn get_sweep_fn(int d);
 

@@ -24,4 +24,11 @@ int CGLB_CAT(sweep_d, CGLB_KMV_D)(Context* ctx, int kind, int mode, const SweepA
     }
 }
 
+
+int CGLB_CAT(knm_d, CGLB_KMV_D)(Context* ctx, int kind, int bwd, const KnmArgs& a, cudaStream_t st) {
+    constexpr int D = CGLB_KMV_D;
+    if (kind == CGLB_MATERN32) return run_knm<CGLB_MATERN32, D>(ctx, bwd, a, st);
+    return run_knm<CGLB_RBF, D>(ctx, bwd, a, st);
+}
+
 }  // namespace cglb

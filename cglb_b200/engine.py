@@ -1,0 +1,193 @@
+"""Torch-tensor level wrappers over the C-ABI (include/cglb_b200.h).
+
+`Engine` owns one `cglb_context` per CUDA device and exposes each entry point with torch tensors in
+place of raw pointers.  torch is used for device memory, streams and (in distributed.py) NCCL only; all
+arithmetic on n-sized or M x n-sized data runs in libcglb_b200.so.  There is no CPU path: tensors must
+live on a CUDA device and the shared library must be built, otherwise `CglbError` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _ffi
+from ._ffi import CglbError, KIND_IDS, check, ptr
+
+Tensor = torch.Tensor
+
+_ENGINES: Dict[int, "Engine"] = {}
+
+
+def get_engine(device=None) -> "Engine":
+    """One Engine (one cglb_context) per CUDA device."""
+    if not torch.cuda.is_available():
+        raise CglbError("cglb_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise CglbError(f"cglb_b200 tensors must live on a CUDA device, got {device}")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    eng = _ENGINES.get(idx)
+    if eng is None:
+        eng = Engine(idx)
+        _ENGINES[idx] = eng
+    return eng
+
+
+def _req(t: Tensor, name: str, dtype=torch.float64):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise CglbError(f"{name}: expected a CUDA tensor (cglb_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise CglbError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise CglbError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+class Engine:
+    def __init__(self, device_index: int):
+        self.lib = _ffi.load_library()
+        self.device = torch.device("cuda", device_index)
+        handle = C.c_void_p()
+        check(self.lib.cglb_create(C.byref(handle), device_index), "cglb_create")
+        self.ctx = handle
+
+    # ---- bookkeeping ---------------------------------------------------------------------------
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.cglb_launch_count(self.ctx))
+
+    @property
+    def num_sms(self) -> int:
+        return int(self.lib.cglb_num_sms(self.ctx))
+
+    def packed_width(self, d: int) -> int:
+        return int(self.lib.cglb_packed_width(d))
+
+    def padded_rows(self, n: int) -> int:
+        return int(self.lib.cglb_padded_rows(n))
+
+    def empty(self, *shape, dtype=torch.float64) -> Tensor:
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float64) -> Tensor:
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    # ---- K7 prep ---------------------------------------------------------------------------------
+    def pack(self, kind: str, x: Tensor, lengthscale: Tensor, shift: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
+        _req(x, "x"); _req(lengthscale, "lengthscale")
+        n, d = x.shape
+        if lengthscale.numel() != d:
+            raise CglbError("lengthscale must have one entry per input dimension (ARD)")
+        if out is None:
+            out = self.empty(self.padded_rows(n), self.packed_width(d))
+        check(self.lib.cglb_pack_inputs(self.ctx, KIND_IDS[kind], ptr(x), n, d, ptr(lengthscale),
+                                        ptr(shift) if shift is not None else None, ptr(out), self.stream()), "cglb_pack_inputs")
+        return out
+
+    # ---- K1 / K2 ------------------------------------------------------------------------------------
+    def kmv_sym(self, kind, xp, n, d, v, variance, diag, out=None, part=0, nparts=1) -> Tensor:
+        _req(xp, "xp"); _req(v, "v")
+        if out is None:
+            out = self.empty(n)
+        check(self.lib.cglb_kmv_sym(self.ctx, KIND_IDS[kind], ptr(xp), n, d, ptr(v), ptr(out), float(variance), float(diag),
+                                    int(part), int(nparts), self.stream()), "cglb_kmv_sym")
+        return out
+
+    def kmv_rect(self, kind, xp_rows, nrows, xp_cols, ncols, d, v, variance, out=None) -> Tensor:
+        _req(xp_rows, "xp_rows"); _req(xp_cols, "xp_cols"); _req(v, "v")
+        if out is None:
+            out = self.empty(nrows)
+        check(self.lib.cglb_kmv_rect(self.ctx, KIND_IDS[kind], ptr(xp_rows), nrows, ptr(xp_cols), ncols, d, ptr(v), ptr(out),
+                                     float(variance), self.stream()), "cglb_kmv_rect")
+        return out
+
+    def kmv_bwd_sym(self, kind, xp, n, d, u, w, variance, lengthscale, out, part=0, nparts=1) -> Tensor:
+        _req(xp, "xp"); _req(u, "u"); _req(w, "w"); _req(lengthscale, "lengthscale"); _req(out, "out")
+        check(self.lib.cglb_kmv_bwd_sym(self.ctx, KIND_IDS[kind], ptr(xp), n, d, ptr(u), ptr(w), float(variance),
+                                        ptr(lengthscale), ptr(out), int(part), int(nparts), self.stream()), "cglb_kmv_bwd_sym")
+        return out
+
+    # ---- K7 -------------------------------------------------------------------------------------------
+    def knm_build(self, kind, zp, m, xp, n, d, variance, out, ld) -> Tensor:
+        _req(zp, "zp"); _req(xp, "xp"); _req(out, "out")
+        check(self.lib.cglb_knm_build(self.ctx, KIND_IDS[kind], ptr(zp), m, ptr(xp), n, d, float(variance), ptr(out), ld,
+                                      self.stream()), "cglb_knm_build")
+        return out
+
+    def knm_backward(self, kind, zp, m, xp, ncols, d, variance, lengthscale, t, ldt, wt, zvec, out_ls, out_var, out_z):
+        check(self.lib.cglb_knm_backward(self.ctx, KIND_IDS[kind], ptr(zp), m, ptr(xp), ncols, d, float(variance),
+                                         ptr(lengthscale), ptr(t), ldt, ptr(wt), ptr(zvec), ptr(out_ls), ptr(out_var),
+                                         ptr(out_z), self.stream()), "cglb_knm_backward")
+
+    # ---- K5 / K6 --------------------------------------------------------------------------------------
+    def potrf(self, a: Tensor, what: str = "matrix") -> Tensor:
+        """In-place lower Cholesky of a square matrix; raises like torch.cholesky on failure
+        (the reference lets the RuntimeError propagate)."""
+        _req(a, "a")
+        m = a.shape[0]
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(self.lib.cglb_potrf(self.ctx, ptr(a), m, a.stride(0), ptr(info), self.stream()), "cglb_potrf")
+        bad = int(info.item())
+        if bad != 0:
+            raise RuntimeError(f"cholesky: {what} is not positive definite (block {bad - 1})")
+        return a
+
+    def tri_inverse(self, l: Tensor, out: Optional[Tensor] = None) -> Tensor:
+        _req(l, "l")
+        m = l.shape[0]
+        if out is None:
+            out = self.empty(m, m)
+        check(self.lib.cglb_tri_inverse(self.ctx, ptr(l), m, l.stride(0), ptr(out), out.stride(0), self.stream()), "cglb_tri_inverse")
+        return out
+
+    def trsm_left_lower(self, l: Tensor, b: Tensor, n: int, alpha: float = 1.0) -> Tensor:
+        _req(l, "l"); _req(b, "b")
+        check(self.lib.cglb_trsm_left_lower(self.ctx, ptr(l), l.shape[0], l.stride(0), ptr(b), n, b.stride(0), float(alpha),
+                                            self.stream()), "cglb_trsm_left_lower")
+        return b
+
+    def syrk(self, a: Tensor, m: int, n: int, out: Tensor, accumulate: bool = False) -> Tensor:
+        _req(a, "a"); _req(out, "out")
+        check(self.lib.cglb_syrk(self.ctx, ptr(a), m, n, a.stride(0), ptr(out), out.stride(0), int(accumulate), self.stream()), "cglb_syrk")
+        return out
+
+    def gemm(self, a: Tensor, b: Tensor, out: Tensor, m: int, n: int, k: int, transb: bool = False, alpha: float = 1.0,
+             beta: float = 0.0) -> Tensor:
+        _req(a, "a"); _req(b, "b"); _req(out, "out")
+        check(self.lib.cglb_gemm(self.ctx, int(transb), m, n, k, float(alpha), ptr(a), a.stride(0), ptr(b), b.stride(0),
+                                 float(beta), ptr(out), out.stride(0), self.stream()), "cglb_gemm")
+        return out
+
+    # ---- K3 / K4 --------------------------------------------------------------------------------------
+    def precond_project(self, a: Tensor, m: int, ncols: int, r: Tensor, q: Tensor) -> Tensor:
+        check(self.lib.cglb_precond_project(self.ctx, ptr(a), m, ncols, a.stride(0), ptr(r), ptr(q), self.stream()), "cglb_precond_project")
+        return q
+
+    def precond_finish(self, a: Tensor, m: int, ncols: int, lbinv: Tensor, q: Tensor, r: Tensor, sigma_sq: float,
+                       z: Tensor, w: Tensor, rz: Tensor):
+        check(self.lib.cglb_precond_finish(self.ctx, ptr(a), m, ncols, a.stride(0), ptr(lbinv), ptr(q), ptr(r), float(sigma_sq),
+                                           ptr(z), ptr(w), ptr(rz), self.stream()), "cglb_precond_finish")
+
+    # ---- K8 -------------------------------------------------------------------------------------------
+    def dot(self, x: Tensor, y: Tensor, out: Tensor) -> Tensor:
+        check(self.lib.cglb_dot(self.ctx, ptr(x), ptr(y), x.numel(), ptr(out), self.stream()), "cglb_dot")
+        return out
+
+    def cg_step(self, n, rz, pAp, p, Ap, v, r, restart: bool):
+        check(self.lib.cglb_cg_step(self.ctx, n, ptr(rz), ptr(pAp), ptr(p), ptr(Ap), ptr(v), ptr(r), int(restart), self.stream()), "cglb_cg_step")
+
+    def residual(self, n, b, Av, r):
+        check(self.lib.cglb_residual(self.ctx, n, ptr(b), ptr(Av), ptr(r), self.stream()), "cglb_residual")
+
+    def cg_direction(self, n, z, p, rz_new, rz_old, restart: bool):
+        check(self.lib.cglb_cg_direction(self.ctx, n, ptr(z), ptr(p), ptr(rz_new), ptr(rz_old), int(restart), self.stream()), "cglb_cg_direction")
+
+    def quad_terms(self, n, err, Kv, v, r, out):
+        check(self.lib.cglb_quad_terms(self.ctx, n, ptr(err), ptr(Kv), ptr(v), ptr(r), ptr(out), self.stream()), "cglb_quad_terms")
