@@ -1,6 +1,6 @@
 """Build libcglb_b200.so (sm_100a only) in-tree with nvcc.
 
-    python -m cglb_b200.build            # all kernels, d = 1..16
+    python -m cglb_b200.build            # all kernels, d = 1..32
     CGLB_KMV_DIMS=3,8,11 python -m cglb_b200.build   # quick developer build
 
 Objects go to cglb_b200/csrc/build/, the shared library to cglb_b200/lib/libcglb_b200.so (git-ignored,
@@ -26,7 +26,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr"]
 PLAIN_UNITS = ["context.cu", "kmv_api.cu", "dense.cu", "vecops.cu", "knm.cu", "widek.cu"]
-ALL_DIMS = list(range(1, 17))
+ALL_DIMS = list(range(1, 33))
 
 
 def _dims():

@@ -36,6 +36,18 @@ struct GemmArgs {
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+// 16-byte chunk = two doubles; falls back to two 8-byte copies when the operand is not 16-byte aligned
+__device__ __forceinline__ void cp_chunk(bool vec, double* smem, const double* src, int bytes) {
+    if (vec) {
+        cp_async16(smem, src, bytes);
+    } else {
+        cp_async8(smem, src, bytes >= 8 ? 8 : 0);
+        cp_async8(smem + 1, bytes == 16 ? src + 1 : src, bytes == 16 ? 8 : 0);
+    }
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -71,6 +83,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp >> 2, wn = warp & 3;
 
+    const bool a_vec = ((p.lda & 1) == 0) && (((uintptr_t)p.A & 15) == 0);
+    const bool b_vec = ((p.ldb & 1) == 0) && (((uintptr_t)p.B & 15) == 0);
     auto load_tile = [&](int kt, int stage) {
         const long k0 = kbeg + (long)kt * GK;
         double* a = sA + stage * GemmSmem<TRANSB>::kA;
@@ -83,7 +97,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
             long rem = kend - gk;
             int bytes = (gr < p.m && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
             const double* src = bytes ? p.A + gr * p.lda + gk : p.A;
-            cp_async16(a + row * GPITCH_K + kc, src, bytes);
+            cp_chunk(a_vec, a + row * GPITCH_K + kc, src, bytes);
         }
         if (TRANSB) {
 #pragma unroll
@@ -94,7 +108,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
                 long rem = kend - gk;
                 int bytes = (gr < p.n && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
                 const double* src = bytes ? p.B + gr * p.ldb + gk : p.B;
-                cp_async16(b + row * GPITCH_K + kc, src, bytes);
+                cp_chunk(b_vec, b + row * GPITCH_K + kc, src, bytes);
             }
         } else {
 #pragma unroll
@@ -105,7 +119,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
                 long rem = p.n - gc;
                 int bytes = (gk < kend && rem > 0) ? (rem >= 2 ? 16 : 8) : 0;
                 const double* src = bytes ? p.B + gk * p.ldb + gc : p.B;
-                cp_async16(b + row * GPITCH_N + nc, src, bytes);
+                cp_chunk(b_vec, b + row * GPITCH_N + nc, src, bytes);
             }
         }
     };
@@ -190,8 +204,6 @@ static int launch_gemm(Context* ctx, const GemmArgs& p, int ksplit, cudaStream_t
 
 static int gemm_checked(Context* ctx, int transb, long m, long n, long k, double alpha, const double* a, long lda,
                         const double* b, long ldb, double beta, double* c, long ldc, cudaStream_t st) {
-    CGLB_CHECK_ARG(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0), "gemm operands must be 16-byte aligned");
-    CGLB_CHECK_ARG(lda % 2 == 0 && ldb % 2 == 0, "gemm leading dimensions must be even");
     GemmArgs p{a, lda, b, ldb, c, ldc, m, n, k, (k + GK - 1) / GK * GK, alpha, beta, 0};
     if (p.k_chunk == 0) p.k_chunk = GK;
     return transb ? launch_gemm<true, EPI_STORE>(ctx, p, 1, st) : launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
@@ -375,7 +387,6 @@ extern "C" int cglb_syrk(cglb_context* c, const double* a, long m, long n, long 
                          void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);
     CGLB_CHECK_ARG(ctx && a && cm, "null pointer");
-    CGLB_CHECK_ARG(((uintptr_t)a % 16 == 0) && lda % 2 == 0, "syrk operand alignment");
     cudaStream_t st = (cudaStream_t)stream;
     if (m == 0) return CGLB_OK;
     if (!accumulate) {
@@ -401,7 +412,6 @@ extern "C" int cglb_syrk(cglb_context* c, const double* a, long m, long n, long 
 extern "C" int cglb_potrf(cglb_context* c, double* a, long m, long lda, int* info_dev, void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);
     CGLB_CHECK_ARG(ctx && a && info_dev, "null pointer");
-    CGLB_CHECK_ARG(((uintptr_t)a % 16 == 0) && lda % 2 == 0, "potrf operand alignment");
     cudaStream_t st = (cudaStream_t)stream;
     if (m == 0) return CGLB_OK;
     DenseWs ws;
@@ -435,7 +445,6 @@ extern "C" int cglb_potrf(cglb_context* c, double* a, long m, long lda, int* inf
 extern "C" int cglb_tri_inverse(cglb_context* c, const double* l, long m, long ldl, double* linv, long ldi, void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);
     CGLB_CHECK_ARG(ctx && l && linv, "null pointer");
-    CGLB_CHECK_ARG(((uintptr_t)l % 16 == 0) && ((uintptr_t)linv % 16 == 0) && ldl % 2 == 0 && ldi % 2 == 0, "alignment");
     cudaStream_t st = (cudaStream_t)stream;
     if (m == 0) return CGLB_OK;
     DenseWs ws;
@@ -467,7 +476,6 @@ extern "C" int cglb_trsm_left_lower(cglb_context* c, const double* l, long m, lo
                                     double alpha, void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);
     CGLB_CHECK_ARG(ctx && l && b, "null pointer");
-    CGLB_CHECK_ARG(((uintptr_t)l % 16 == 0) && ((uintptr_t)b % 16 == 0) && ldl % 2 == 0 && ldb % 2 == 0, "alignment");
     cudaStream_t st = (cudaStream_t)stream;
     if (m == 0 || n == 0) return CGLB_OK;
     DenseWs ws;

@@ -70,7 +70,9 @@ __global__ void bwd_epilogue_kernel(const double* __restrict__ xp, long n, int d
 
 // CGLB_KMV_DIMS_LIST = "X(1) X(2) ..." : the dimensions this build instantiates (build.py passes it)
 #ifndef CGLB_KMV_DIMS_LIST
-#define CGLB_KMV_DIMS_LIST X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#define CGLB_KMV_DIMS_LIST                                                                                 \
+    X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19) X(20) \
+        X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
 #endif
 #define X(DD)                                                              \
     int sweep_d##DD(Context*, int, int, const SweepArgs&, cudaStream_t);   \
@@ -136,10 +138,11 @@ extern "C" int cglb_pack_inputs(cglb_context* c, int kind, const double* x, long
 extern "C" int cglb_kmv_sym(cglb_context* c, int kind, const double* xp, long n, int d, const double* v, double* y,
                             double variance, double diag, int part, int nparts, void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);
-    CGLB_CHECK_ARG(ctx && xp && v && y, "null pointer");
+    CGLB_CHECK_ARG(ctx != nullptr, "null context");
     CGLB_CHECK_ARG(nparts >= 1 && part >= 0 && part < nparts, "part/nparts");
     CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
-    if (n == 0) return CGLB_OK;
+    if (n == 0) return CGLB_OK;      // empty input: nothing to do (pointers may be null)
+    CGLB_CHECK_ARG(xp && v && y, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     long n_pad = padded_rows(n);
     // the symmetric sweep reads rows in blocks of up to 1024: pad the vector accordingly
@@ -159,9 +162,10 @@ extern "C" int cglb_kmv_sym(cglb_context* c, int kind, const double* xp, long n,
 extern "C" int cglb_kmv_rect(cglb_context* c, int kind, const double* xp_rows, long nrows, const double* xp_cols,
                              long ncols, int d, const double* v, double* y, double variance, void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);
-    CGLB_CHECK_ARG(ctx && xp_rows && xp_cols && v && y, "null pointer");
+    CGLB_CHECK_ARG(ctx != nullptr, "null context");
     CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
     if (nrows == 0) return CGLB_OK;
+    CGLB_CHECK_ARG(xp_rows && y && (ncols == 0 || (xp_cols && v)), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     long v_pad = (ncols + 1023) / 1024 * 1024;
     int rc = ensure_vpad(ctx, v_pad);
@@ -181,10 +185,11 @@ extern "C" int cglb_kmv_bwd_sym(cglb_context* c, int kind, const double* xp, lon
                                 const double* w, double variance, const double* lengthscale, double* out, int part,
                                 int nparts, void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);
-    CGLB_CHECK_ARG(ctx && xp && u && w && out && lengthscale, "null pointer");
+    CGLB_CHECK_ARG(ctx != nullptr, "null context");
     CGLB_CHECK_ARG(nparts >= 1 && part >= 0 && part < nparts, "part/nparts");
     CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
     if (n == 0) return CGLB_OK;
+    CGLB_CHECK_ARG(xp && u && w && out && lengthscale, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     long v_pad = (n + 1023) / 1024 * 1024;
     int rc = ensure_vpad(ctx, v_pad);

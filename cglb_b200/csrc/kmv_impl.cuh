@@ -485,7 +485,8 @@ struct KnmArgs {
 };
 
 constexpr int kKnmRows = 64;           // rows of Z per CTA (build)
-constexpr int kKnmBwdRows = 32;        // rows of Z per CTA (backward: per-warp partial slabs live in smem)
+// rows of Z per CTA in the backward: the per-warp partial slabs [8][rows][CGR] must fit in 48 KB of static smem
+__host__ __device__ constexpr int knm_bwd_rows(int d) { return d <= 16 ? 32 : 16; }
 
 template <int KIND, int D>
 __global__ void __launch_bounds__(256) knm_build_kernel(const KnmArgs args) {
@@ -528,7 +529,8 @@ __global__ void __launch_bounds__(256) knm_build_kernel(const KnmArgs args) {
 template <int KIND, int D>
 __global__ void __launch_bounds__(256) knm_bwd_kernel(const KnmArgs args) {
     constexpr int DP = SmemLayout<D>::DP;
-    constexpr int CGR = D <= 1 ? 1 : D <= 2 ? 2 : D <= 4 ? 4 : D <= 8 ? 8 : 16;
+    constexpr int CGR = D <= 1 ? 1 : D <= 2 ? 2 : D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
+    constexpr int kKnmBwdRows = knm_bwd_rows(D);
     __shared__ __align__(16) double s_z[kKnmBwdRows * DP];
     __shared__ double s_tab[64];
     __shared__ double s_wt[kKnmBwdRows];
@@ -620,7 +622,7 @@ __global__ void __launch_bounds__(256) knm_bwd_kernel(const KnmArgs args) {
 template <int KIND, int D>
 static int run_knm(Context* ctx, int bwd, const KnmArgs& a, cudaStream_t st) {
     if (a.m <= 0 || a.ncols <= 0) return CGLB_OK;
-    const int rows = bwd ? kKnmBwdRows : kKnmRows;
+    const int rows = bwd ? knm_bwd_rows(D) : kKnmRows;
     dim3 grid((unsigned)((a.ncols + 255) / 256), (unsigned)((a.m + rows - 1) / rows));
     if (bwd) knm_bwd_kernel<KIND, D><<<grid, 256, 0, st>>>(a);
     else knm_build_kernel<KIND, D><<<grid, 256, 0, st>>>(a);
@@ -718,7 +720,7 @@ static int run_bwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
 typedef int (*sweep_fn)(Context*, int kind, int mode /*0 sym fwd, 1 rect fwd, 2 sym bwd*/, const SweepArgs&, cudaStream_t);
 typedef int (*knm_fn)(Context*, int kind, int bwd, const KnmArgs&, cudaStream_t);
 knm_fn get_knm_fn(int d);
-constexpr int kMaxRegisterD = 16;
+constexpr int kMaxRegisterD = 32;
 sweep_fn get_sweep_fn(int d);
 
 }  // namespace cglb

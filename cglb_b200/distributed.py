@@ -1,0 +1,76 @@
+"""Row sharding of the hot path over the GPUs of one box.
+
+One process per GPU (`torch.distributed`, NCCL over NVLink 5 / NVSwitch).  What is sharded:
+  * the work items of the matrix-free sweeps (K v, backward sweep): rank g processes the tile pairs
+    {t : t % world == g} of the symmetric enumeration (csrc/kmv_impl.cuh) and the partial n-vectors are
+    all-reduced -- with the symmetric sweep a tile contributes to two row blocks, so the exchange is an
+    all-reduce of y rather than an all-gather of p;
+  * the columns of the dense M x n matrix A = L^-1 K_uf / sigma (rows of K_nm): rank g owns the
+    contiguous column block [lo_g, hi_g).
+Replicated: X, y, Z, every n-vector of the solver (16 MB at n = 2M), all M x M factors.  Because every
+all-reduced quantity is bit-identical on all ranks, all ranks take the same CG branches.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Optional, Tuple
+
+import torch
+
+try:
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    dist = None
+
+
+@dataclass
+class Shard:
+    rank: int = 0
+    world: int = 1
+    group: Any = None
+
+    @staticmethod
+    def from_env() -> "Shard":
+        """The default process group if torch.distributed is initialised, else a single shard."""
+        if dist is not None and dist.is_available() and dist.is_initialized():
+            return Shard(dist.get_rank(), dist.get_world_size(), None)
+        return Shard()
+
+    # ---- partition arithmetic (pure python; covered by the CPU gloo tests) --------------------------
+    def column_block(self, n: int) -> Tuple[int, int]:
+        """Contiguous, even-aligned column block [lo, hi) of an n-column matrix owned by this rank."""
+        per = -(-n // self.world)
+        per += per & 1
+        lo = min(self.rank * per, n)
+        hi = min(lo + per, n)
+        return lo, hi
+
+    def owns_item(self, t: int) -> bool:
+        """Same rule as the kernels: global work item t belongs to part t % world."""
+        return t % self.world == self.rank
+
+    # ---- collectives ---------------------------------------------------------------------------------
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+
+def symmetric_items(n: int, block: int):
+    """Enumeration of the symmetric sweep's work items: t = C(C+1)/2 + I for row block I <= column
+    block C (must match item_to_blocks_sym in csrc/kmv_impl.cuh)."""
+    nb = -(-n // block)
+    t = 0
+    for c in range(nb):
+        for i in range(c + 1):
+            yield t, i, c
+            t += 1

@@ -1,0 +1,270 @@
+"""GPU (-m gpu): parity of the sm_100a path, called through the C-ABI, against the CPU oracle and the golden
+vectors produced by the reference's own code.  Tolerances are the north_star's: per-matvec relative error
+<= 1e-10, bound and gradients <= 1e-7 relative, CG iteration count within +-1."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cglb_b200 as cb
+from conftest import GOLDEN_CASES, GOLDEN_DIR, GRAD_NAMES
+from helpers import make_model, rel_max
+from oracle import cglb_oracle as o
+
+pytestmark = pytest.mark.gpu
+f64 = torch.float64
+MATVEC_TOL = 1e-10
+BOUND_TOL = 1e-7
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from cglb_b200.engine import get_engine
+    return get_engine()
+
+
+def _problem(n, d, seed, lsval=None):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, d, generator=g, dtype=f64)
+    v = torch.randn(n, generator=g, dtype=f64)
+    u = torch.randn(n, generator=g, dtype=f64)
+    ls = (torch.rand(d, generator=g, dtype=f64) + 0.5) * (lsval if lsval else 0.5 * math.sqrt(d))
+    return x, v, u, ls
+
+
+# ---- K1: matvec ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n,d", [("matern32", 1, 1), ("matern32", 2, 3), ("matern32", 300, 1), ("rbf", 777, 8),
+                                      ("matern32", 2500, 11), ("rbf", 2049, 3), ("matern32", 1025, 5), ("rbf", 900, 16),
+                                      ("matern32", 640, 20), ("rbf", 513, 32), ("matern32", 1300, 13)])
+def test_kmv_sym_matches_oracle(eng, kind, n, d):
+    x, v, u, ls = _problem(n, d, seed=n + d)
+    dev = eng.device
+    xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    y = eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.3, 0.07)
+    K = o.kernel_dense(kind, x, x, ls, torch.tensor(1.3, dtype=f64))
+    ref = K @ v + 0.07 * v
+    assert float((y.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
+    # work-item partition (what each rank of a row-sharded run computes) sums to the full product
+    parts = sum(eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.3, 0.07, part=p, nparts=3) for p in range(3))
+    assert float((parts.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
+
+
+@pytest.mark.parametrize("kind,d,lsval", [("matern32", 3, 0.05), ("rbf", 3, 0.05), ("matern32", 8, 30.0)])
+def test_kmv_extreme_lengthscales(eng, kind, d, lsval):
+    """expanded-form distances must survive tiny lengthscales (huge |a|^2) and huge ones (K ~ all ones)."""
+    n = 1500
+    x, v, u, ls = _problem(n, d, seed=5, lsval=lsval)
+    dev = eng.device
+    xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    y = eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.0, 0.0)
+    ref = o.kernel_dense(kind, x, x, ls, torch.tensor(1.0, dtype=f64)) @ v
+    assert float((y.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
+
+
+def test_kmv_duplicate_points_and_empty(eng):
+    dev = eng.device
+    x = torch.randn(40, 2, dtype=f64, generator=torch.Generator().manual_seed(1)).repeat(8, 1)   # exact duplicates
+    n, d = x.shape
+    ls = torch.tensor([0.9, 1.1], dtype=f64)
+    v = torch.randn(n, dtype=f64, generator=torch.Generator().manual_seed(2))
+    for kind in ("matern32", "rbf"):
+        xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+        y = eng.kmv_sym(kind, xp, n, d, v.to(dev), 2.0, 0.5)
+        ref = o.kernel_dense(kind, x, x, ls, torch.tensor(2.0, dtype=f64)) @ v + 0.5 * v
+        assert float((y.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
+    y0 = eng.kmv_sym("rbf", eng.empty(0, 4), 0, 2, eng.empty(0), 1.0, 0.0, out=eng.empty(0))
+    assert y0.numel() == 0
+
+
+@pytest.mark.parametrize("kind,nr,nc,d", [("matern32", 100, 1000, 3), ("rbf", 1500, 333, 8), ("matern32", 64, 3000, 11),
+                                          ("matern32", 7, 129, 20)])
+def test_kmv_rect_matches_oracle(eng, kind, nr, nc, d):
+    g = torch.Generator().manual_seed(nr + nc)
+    xr, xc = torch.randn(nr, d, generator=g, dtype=f64), torch.randn(nc, d, generator=g, dtype=f64)
+    v = torch.randn(nc, generator=g, dtype=f64)
+    ls = torch.rand(d, generator=g, dtype=f64) + 0.8
+    dev = eng.device
+    shift = xc.mean(0).to(dev)
+    y = eng.kmv_rect(kind, eng.pack(kind, xr.to(dev), ls.to(dev), shift), nr, eng.pack(kind, xc.to(dev), ls.to(dev), shift), nc, d,
+                     v.to(dev), 0.9)
+    ref = o.kernel_dense(kind, xr, xc, ls, torch.tensor(0.9, dtype=f64)) @ v
+    assert float((y.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
+
+
+# ---- K2: backward sweep ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n,d", [("matern32", 300, 1), ("rbf", 777, 8), ("matern32", 2500, 11), ("rbf", 1030, 3),
+                                      ("matern32", 520, 20), ("rbf", 300, 32)])
+def test_backward_sweep_matches_autograd(eng, kind, n, d):
+    x, v, u, ls = _problem(n, d, seed=3 * n + d)
+    dev = eng.device
+    xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    out = eng.zeros(d + 1)
+    eng.kmv_bwd_sym(kind, xp, n, d, u.to(dev), v.to(dev), 1.3, ls.to(dev), out)
+    lsr, varr = ls.clone().requires_grad_(True), torch.tensor(1.3, dtype=f64, requires_grad=True)
+    f = u @ (o.kernel_dense(kind, x, x, lsr, varr) @ v)
+    gl, gv = torch.autograd.grad(f, [lsr, varr])
+    ref = torch.cat([gl.reshape(-1), gv.reshape(1)])
+    assert float((out.cpu() - ref).norm() / ref.norm()) <= 1e-9
+    parts = eng.zeros(d + 1)
+    for p in range(2):
+        eng.kmv_bwd_sym(kind, xp, n, d, u.to(dev), v.to(dev), 1.3, ls.to(dev), parts, part=p, nparts=2)
+    assert float((parts.cpu() - ref).norm() / ref.norm()) <= 1e-9
+
+
+def test_operator_protocol_with_autograd(eng):
+    """`kernel(x).add_diag(s2) @ v` (models.py:251-252,280) is differentiable w.r.t. the kernel parameters."""
+    x, y, z = o.synthetic_problem(400, 3, 8, seed=2)
+    model = make_model("matern32", x.numpy(), y.numpy(), z.numpy(), 0.2, 1.4, [0.7, 1.0, 1.2])
+    kern = model.covar_module.base_kernel
+    xd = model.train_inputs[0]
+    v = torch.randn(400, 1, dtype=f64, device=xd.device, generator=torch.Generator(device=xd.device).manual_seed(0))
+    cov = kern(xd).add_diag(model.likelihood.noise.squeeze())
+    out = cov @ v
+    g = torch.autograd.grad((out * out).sum(), [kern.raw_outputscale, kern.base_kernel.raw_lengthscale, model.likelihood.noise_covar.raw_noise])
+    p = o.OracleParams.from_values(0.2, 0.0, z, 1.4, [0.7, 1.0, 1.2])
+    K = o.kernel_dense("matern32", x, x, p.lengthscale, p.variance) + p.noise * torch.eye(400, dtype=f64)
+    ref_out = K @ v.cpu()
+    gref = torch.autograd.grad((ref_out * ref_out).sum(), [p.raw_outputscale, p.raw_lengthscale, p.raw_noise])
+    assert rel_max(out.detach().cpu().numpy(), ref_out.detach().numpy()) <= MATVEC_TOL
+    for a, b in zip(g, gref):
+        assert rel_max(a.cpu().numpy(), b.numpy()) <= 1e-8
+    assert rel_max((cov.detach() @ v).cpu().numpy(), ref_out.detach().numpy()) <= MATVEC_TOL
+    dense = kern(model.covar_module.inducing_points.detach(), xd).evaluate()
+    kref = o.kernel_dense("matern32", z, x, p.lengthscale.detach(), p.variance.detach())
+    assert rel_max(dense.cpu().numpy(), kref.numpy()) <= 1e-12
+
+
+# ---- solver API --------------------------------------------------------------------------------------------------------
+def test_conjugate_gradient_and_preconditioner_on_reference_golden_system():
+    g = np.load(os.path.join(GOLDEN_DIR, "cg_dense_system.npz"))
+    dev = torch.device("cuda")
+    K, A, LB, b = (torch.from_numpy(g[k]).to(dev) for k in ("K", "A", "LB", "b"))
+    pre = cb.NystromPreconditioner(A, LB, torch.tensor(float(g["sigma_sq"]), dtype=f64, device=dev))
+    z, rz = pre(b)
+    assert rel_max(z.cpu().numpy(), g["precond_z"]) < 1e-11
+    assert abs(float(rz) - float(g["precond_rz"])) < 1e-11 * abs(float(g["precond_rz"]))
+    for tag, kw in [("default", {}), ("tight", dict(max_error=1e-6)), ("restart", dict(max_error=1e-9, restart_cg_iter=5, max_cg_iter=23))]:
+        v, st = cb.ConjugateGradient(**kw)(K, b, torch.zeros_like(b), pre)
+        assert abs(int(st.steps) - int(g[f"steps_{tag}"])) <= 1
+        assert rel_max(v.cpu().numpy(), g[f"v_{tag}"]) < 1e-4
+        if tag == "default" and int(st.steps) == int(g[f"steps_{tag}"]):
+            # (near machine-precision convergence, the "tight" case, the final residual is rounding noise)
+            assert abs(float(st.residual_error) - float(g[f"err_{tag}"])) <= 1e-3 * abs(float(g[f"err_{tag}"]))
+
+
+# ---- objective: golden vectors of the reference's own LowerBoundCG -------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_bound_and_gradients_match_reference_golden(name):
+    g = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    kind = str(g["kind"])
+    model = make_model(kind, g["x"], g["y"], g["z"], float(g["noise"]), float(g["variance"]), g["lengthscale"], float(g["mean_c"]))
+    cg = cb.ConjugateGradient(max_error=float(g["cg_max_error"]), max_cg_iter=int(g["cg_max_iter"]), restart_cg_iter=int(g["cg_restart"]))
+    lb = cb.LowerBoundCG(model, cg_opt=cg)
+    data = (model.train_inputs[0], model.train_targets)
+    params = list(model.parameters())
+    for e, mult in enumerate(g["ls_mults"]):
+        model.covar_module.base_kernel.base_kernel.lengthscale = torch.as_tensor(g["lengthscale"] * mult)
+        loss = -lb(data)
+        grads = torch.autograd.grad(loss, params)                                  # optimizer.py:95-98
+        ref = float(g[f"loss_{e}"])
+        assert abs(float(loss) - ref) <= BOUND_TOL * abs(ref)
+        assert abs(int(model.cg_stats.steps) - int(g[f"cg_steps_{e}"])) <= 1
+        if int(model.cg_stats.steps) == int(g[f"cg_steps_{e}"]):
+            assert rel_max(model.v_vec.cpu().numpy(), g[f"v_{e}"]) < 1e-4
+            for nm, gr in zip(GRAD_NAMES, grads):
+                refg = g[f"grad_{nm}_{e}"]
+                assert np.abs(gr.cpu().numpy() - refg).max() <= BOUND_TOL * np.abs(refg).max() + 1e-9, (name, e, nm)
+
+
+@pytest.mark.parametrize("kind,n,d,M,noise", [("matern32", 900, 3, 40, 0.05), ("rbf", 700, 8, 33, 0.3), ("matern32", 513, 11, 64, 0.01),
+                                              ("matern32", 400, 20, 24, 0.1)])
+def test_bound_and_gradients_fixed_v_match_oracle(kind, n, d, M, noise):
+    """With CG disabled (use_cache, as the reference's metrics path interface.py:621-625) every term is a
+    deterministic function of v: compare at tight tolerance."""
+    x, y, z = o.synthetic_problem(n, d, M, seed=n)
+    ls = np.linspace(0.8, 1.6, d) * 0.5 * math.sqrt(d)
+    model = make_model(kind, x.numpy(), y.numpy(), z.numpy(), noise, 1.2, ls, 0.05)
+    v = 0.1 * torch.randn(n, 1, dtype=f64, generator=torch.Generator().manual_seed(1))
+    model.v_vec.data.copy_(v.cuda())
+    lb = cb.LowerBoundCG(model, use_cache=True, cached_v_vec_initial=True)
+    loss = -lb((model.train_inputs[0], model.train_targets))
+    grads = torch.autograd.grad(loss, list(model.parameters()))
+    p = o.OracleParams.from_values(noise, 0.05, z, 1.2, ls)
+    res = o.lower_bound(kind, p, x, y, v, use_cached_v=True)
+    ref_grads = torch.autograd.grad(-res.bound, p.tensors())
+    assert abs(float(loss) + float(res.bound)) <= 1e-10 * abs(float(res.bound))
+    for nm, a, b in zip(GRAD_NAMES, grads, ref_grads):
+        assert np.abs(a.cpu().numpy() - b.numpy()).max() <= 1e-8 * np.abs(b.numpy()).max() + 1e-10, nm
+
+
+def test_warm_start_sequence_matches_oracle_iteration_counts():
+    """>= 3 consecutive evaluations with changing hyper-parameters (risk 5)."""
+    n, d, M = 1200, 3, 48
+    x, y, z = o.synthetic_problem(n, d, M, seed=8)
+    model = make_model("matern32", x.numpy(), y.numpy(), z.numpy(), 0.02, 1.0, 0.9)
+    lb = cb.LowerBoundCG(model)
+    for mult in (1.0, 1.01, 0.99, 1.05):
+        # the oracle is warm-started from the SAME vector as the device path: CG amplifies rounding
+        # differences of earlier solves, which is a property of the algorithm, not of the implementation
+        v = model.v_vec.detach().cpu().clone()
+        model.covar_module.base_kernel.base_kernel.lengthscale = torch.full((d,), 0.9 * mult, dtype=f64)
+        loss = -lb((model.train_inputs[0], model.train_targets))
+        p = o.OracleParams.from_values(0.02, 0.0, z, 1.0, 0.9 * mult)
+        res = o.lower_bound("matern32", p, x, y, v)
+        assert abs(int(model.cg_stats.steps) - res.cg.steps) <= 1
+        if int(model.cg_stats.steps) == res.cg.steps:
+            assert abs(float(loss) + float(res.bound)) <= BOUND_TOL * abs(float(res.bound))
+    assert float(model.v_vec.abs().max()) > 0
+
+
+@pytest.mark.parametrize("name", ["road_like_trained", "house_like_warmstart", "snelson_like_init"])
+def test_predict_matches_reference_golden(name):
+    g = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    last = len(g["ls_mults"]) - 1
+    model = make_model(str(g["kind"]), g["x"], g["y"], g["z"], float(g["noise"]), float(g["variance"]),
+                       g["lengthscale"] * g["ls_mults"][last], float(g["mean_c"]))
+    model.v_vec.data.copy_(torch.from_numpy(g[f"v_{last}"]).cuda())
+    pred = cb.PredictCG(model)
+    mean, var = pred(torch.from_numpy(g["xnew"]).cuda())
+    assert rel_max(mean.cpu().numpy(), g["f_mean"]) < 1e-4        # v is only converged to max_error = 1e-3
+    assert rel_max(var.cpu().numpy(), g["f_var"]) < 1e-9
+    mean2, var2 = pred(torch.from_numpy(g["xnew"]).cuda())       # cached path (models.py:323-325)
+    assert torch.allclose(mean, mean2, rtol=1e-12, atol=1e-13) and torch.allclose(var, var2, rtol=1e-12, atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        pred(torch.from_numpy(g["xnew"]).cuda(), full_cov=True)
+
+
+# ---- error behaviour -----------------------------------------------------------------------------------------
+def test_error_behaviour(eng):
+    with pytest.raises(ValueError):
+        cb.LowerBoundCG(torch.nn.Linear(1, 1))
+    bad = -torch.eye(130, dtype=f64, device=eng.device)
+    with pytest.raises(RuntimeError):
+        eng.potrf(bad)
+    with pytest.raises(cb.CglbError):
+        eng.pack("matern32", torch.zeros(4, 2, dtype=f64), torch.ones(2, dtype=f64, device=eng.device), None)
+    with pytest.raises(cb.CglbError):                                # d outside the register-resident range
+        eng.kmv_sym("rbf", eng.zeros(128, 92), 10, 90, eng.zeros(10), 1.0, 0.0)
+
+
+# ---- dense kernels ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [17, 128, 200, 1024])
+def test_dense_factorisations(eng, m):
+    g = torch.Generator().manual_seed(m)
+    xx = torch.randn(m, m + 20, generator=g, dtype=f64).to(eng.device)
+    spd = xx @ xx.t() / m + torch.eye(m, dtype=f64, device=eng.device)
+    l = eng.potrf(spd.clone())
+    lref = torch.linalg.cholesky(spd)
+    assert rel_max(l.cpu().numpy(), lref.cpu().numpy()) < 1e-12
+    linv = eng.tri_inverse(l)
+    assert rel_max((linv @ l).cpu().numpy(), np.eye(m)) < 1e-11
+    n = 333
+    b = torch.randn(m, n + 1, generator=g, dtype=f64).to(eng.device)
+    ref = 0.7 * torch.linalg.solve_triangular(lref, b[:, :n], upper=False)
+    eng.trsm_left_lower(l, b, n, alpha=0.7)
+    assert rel_max(b[:, :n].cpu().numpy(), ref.cpu().numpy()) < 1e-11
+    c = eng.empty(m, m)
+    eng.syrk(b, m, n, c)
+    assert rel_max(c.cpu().numpy(), (b[:, :n] @ b[:, :n].t()).cpu().numpy()) < 1e-12

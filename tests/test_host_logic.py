@@ -1,0 +1,104 @@
+"""CPU: host-side logic that mirrors the reference interface (parameter order and transforms, SciPy
+pack/unpack, configs, inducing-point initialisation, shard arithmetic)."""
+import numpy as np
+import pytest
+import torch
+
+import cglb_b200 as cb
+from cglb_b200.distributed import Shard, symmetric_items
+from cglb_b200.inducing import ConditionalVariance
+from helpers import make_model
+from oracle import cglb_oracle as o
+
+
+def test_parameter_order_shapes_and_transforms():
+    x, y, z = o.synthetic_problem(40, 3, 6)
+    m = make_model("matern32", x.numpy(), y.numpy(), z.numpy(), 0.25, 1.7, [0.5, 1.0, 2.0], 0.3, device="cpu")
+    names = [n for n, _ in m.named_parameters()]
+    assert names == ["likelihood.noise_covar.raw_noise", "mean_module.constant", "covar_module.inducing_points",
+                     "covar_module.base_kernel.raw_outputscale", "covar_module.base_kernel.base_kernel.raw_lengthscale"]
+    shapes = [tuple(p.shape) for p in m.parameters()]
+    assert shapes == [(1,), (1,), (6, 3), (), (1, 3)]
+    assert abs(float(m.likelihood.noise) - 0.25) < 1e-12          # softplus(raw) + 1e-6
+    assert abs(float(m.covar_module.base_kernel.outputscale) - 1.7) < 1e-12
+    assert np.allclose(m.covar_module.base_kernel.base_kernel.lengthscale.detach().numpy(), [[0.5, 1.0, 2.0]])
+    p = o.OracleParams.from_values(0.25, 0.3, z, 1.7, [0.5, 1.0, 2.0])
+    for a, b in zip(m.parameters(), p.tensors()):
+        assert np.allclose(a.detach().numpy(), b.detach().numpy(), atol=1e-12)
+    assert m.v_vec.shape == (40, 1) and not m.v_vec.requires_grad
+    pars = cb.interface.model_parameters(m) if hasattr(cb, "interface") else None
+    from cglb_b200.interface import model_parameters
+    pars = model_parameters(m)
+    assert set(pars) == {".likelihood.variance", ".mean_function.c", ".inducing_variable.Z", ".kernel.lengthscales", ".kernel.variance"}
+
+
+def test_scipy_pack_unpack_assign_roundtrip():
+    ts = [torch.zeros(1, dtype=torch.float64), torch.zeros((), dtype=torch.float64), torch.zeros(2, 3, dtype=torch.float64)]
+    vec = torch.arange(8, dtype=torch.float64)
+    vals = cb.Scipy.unpack(ts, vec)
+    assert [tuple(v.shape) for v in vals] == [(1,), (), (2, 3)]
+    cb.Scipy.assign(ts, vals)
+    assert torch.equal(cb.Scipy.pack(ts), vec)
+    with pytest.raises(ValueError):
+        cb.Scipy.assign(ts, vals[:2])
+
+
+def test_configs_and_registries():
+    data = (np.zeros((5, 4)), np.zeros((5, 1)))
+    assert cb.KERNEL_CONFIGS["mat32"] is cb.Matern32Config and cb.KERNEL_CONFIGS["rbf"] is cb.SquaredExponentialConfig
+    kp = cb.Matern32Config().params(data)
+    assert kp["variance"] == 1.0 and np.allclose(kp["lengthscales"], np.ones(4))
+    cfg = cb.CGLBConfig(kernel=cb.Matern32Config(), inducing_variable=cb.InducingVariableConfig(3))
+    p = cfg.params(data)
+    assert p["noise_variance"] == 1.0 and p["max_error"] == 1.0 and callable(p["inducing_variable"])
+    with pytest.raises(Exception):
+        cfg.max_error = 2.0                                    # frozen
+    from cglb_b200 import interface
+    with pytest.raises(NotImplementedError):
+        interface.set_default_float("fp16")
+    with pytest.raises(NotImplementedError):
+        interface.create_model(object(), data)
+    assert set(cb.BACKENDS) >= {"b200", "torch"}
+    cb.B200.set_default_jitter("fp32")
+    from cglb_b200 import settings
+    assert settings.cholesky_jitter.value() == 1e-5
+    cb.B200.set_default_jitter("fp64")
+    assert settings.cholesky_jitter.value() == 1e-6
+
+
+def test_conditional_variance_greedy_matches_bruteforce():
+    rng = np.random.RandomState(0)
+    X = rng.randn(60, 2)
+    ls = 0.7
+
+    def kern(x1, x2, full_cov=False):
+        if not full_cov:
+            return np.ones(x1.shape[0])
+        x2 = x1 if x2 is None else x2
+        d2 = ((x1[:, None, :] - x2[None, :, :]) ** 2).sum(-1)
+        return np.exp(-0.5 * d2 / ls ** 2)
+
+    Z, idx = ConditionalVariance(sample=False)(X, 8, kern)
+    assert Z.shape == (8, 2) and len(set(idx.tolist())) == 8 and np.allclose(X[idx], Z)
+    # brute force: each new point maximises the conditional variance given the already chosen ones
+    chosen = [idx[0]]
+    for step in range(1, 8):
+        Kzz = kern(X[chosen], X[chosen], True) + 1e-12 * np.eye(len(chosen))
+        Kxz = kern(X, X[chosen], True)
+        cond = 1.0 - np.einsum("ij,jk,ik->i", Kxz, np.linalg.inv(Kzz), Kxz)
+        assert cond[idx[step]] >= cond.max() - 1e-9
+        chosen.append(idx[step])
+
+
+def test_shard_column_blocks_partition_and_items():
+    for n in (1, 7, 300, 2001):
+        for world in (1, 2, 3, 8):
+            blocks = [Shard(r, world).column_block(n) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            for (l0, h0), (l1, h1) in zip(blocks, blocks[1:]):
+                assert h0 == l1 and (l1 % 2 == 0 or l1 == h1)      # non-empty blocks start 16-byte aligned
+    items = list(symmetric_items(1000, 256))
+    assert len(items) == 10 and all(i <= c for _, i, c in items)
+    assert [t for t, _, _ in items] == list(range(10))
+    owned = [sum(Shard(r, 3).owns_item(t) for r in range(3)) for t, _, _ in items]
+    assert owned == [1] * 10
