@@ -92,6 +92,12 @@ class BoundEvaluator:
         self.terms: Optional[CommonTermsDev] = None
         self._packed_key = None
 
+    def refresh_data(self, x: Tensor, y: Tensor):
+        """New contents for the same problem shape (workspaces are kept)."""
+        self.x = x.detach().contiguous()
+        self.y = y.detach().reshape(-1).contiguous()
+        self.shift = self.x.mean(0).contiguous()
+
     # ------------------------------------------------------------------------------------------------
     def _buffers(self, m: int, need_t: bool):
         if self._A is None or self._A.shape[0] != m:
@@ -173,6 +179,23 @@ class BoundEvaluator:
         grads = None
         if need_grad:
             grads = self._gradients(kind, terms, precon, lengthscale, variance, noise, v, z, eb, t)
+        if self.shard.world > 1:
+            # replicated pieces (M x M algebra, K_uu backward) use atomics whose summation order differs
+            # between ranks: publish rank 0's numbers so that every rank's optimiser sees identical values
+            # and takes identical L-BFGS / CG branches
+            keys = ["noise", "mean_c", "Z", "variance", "lengthscale"]
+            flat = [torch.tensor([bound, upper, lower, logdet], dtype=torch.float64, device=self.x.device)]
+            if grads is not None:
+                flat += [grads[k].reshape(-1).to(torch.float64) for k in keys]
+            buf = torch.cat(flat)
+            self.shard.broadcast(buf, src=0)
+            bound, upper, lower, logdet = (float(t_) for t_ in buf[:4].tolist())
+            if grads is not None:
+                off = 4
+                for k in keys:
+                    cnt = grads[k].numel()
+                    grads[k] = buf[off:off + cnt].reshape(grads[k].shape)
+                    off += cnt
         return BoundOutput(bound=bound, upper=-upper, lower=-lower, logdet=logdet, cg_stats=cg_stats,
                            matvecs=op.count, grads=grads)
 

@@ -76,8 +76,9 @@ def build(verbose: bool = True) -> str:
             continue
         defs = [f"-DCGLB_KMV_DIMS_LIST={dims_list}"] if u == "kmv_api.cu" else []
         jobs.append((src, os.path.join(OBJ, u.replace(".cu", ".o")), defs))
+    extra = os.environ.get("CGLB_EXTRA_DEFS", "").split()      # e.g. -DCGLB_KMV_EXPERIMENT (developer builds)
     for d in dims:
-        jobs.append((os.path.join(CSRC, "kmv_inst.cu"), os.path.join(OBJ, f"kmv_d{d}.o"), [f"-DCGLB_KMV_D={d}"]))
+        jobs.append((os.path.join(CSRC, "kmv_inst.cu"), os.path.join(OBJ, f"kmv_d{d}.o"), [f"-DCGLB_KMV_D={d}", *extra]))
     objs = []
     workers = max(1, min(len(jobs), os.cpu_count() or 4))
     with cf.ThreadPoolExecutor(workers) as ex:

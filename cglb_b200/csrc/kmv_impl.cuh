@@ -20,8 +20,8 @@
 
 namespace cglb {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;             // every warp computes; warp 0 / lane 0 also drives TMA
+// every warp computes; lane 0 of warp 0 also drives the TMA ring.  WARPS is a template parameter: 8 warps x 4
+// rows/thread, 12 x 2 or 16 x 2 trade registers (ILP) against resident warps (TLP); see DESIGN.md section 3.
 constexpr int kBJ = 64;                           // columns per pipeline stage
 constexpr int kStages = 4;
 constexpr int kPrefetch = 2;                      // tiles in flight ahead of the one being consumed
@@ -146,7 +146,7 @@ struct Cursor {
 };
 
 // mbarrier ring shared by the forward and backward sweeps.  NVEC = vectors staged per tile (1: v; 2: w,u)
-template <int D, int NVEC>
+template <int D, int NVEC, int WARPS>
 struct TileRing {
     static constexpr int DP = SmemLayout<D>::DP;
     double* s_x;          // [kStages][kBJ*DP]
@@ -159,7 +159,7 @@ struct TileRing {
     __device__ __forceinline__ void init_barriers() {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], kWarps);
+            mbar_init(&s_empty[s], WARPS);
         }
         mbar_fence_init();
     }
@@ -183,7 +183,7 @@ struct TileRing {
     }
 };
 
-template <int D, int DP, int TI>
+template <int D, int DP, int TI, int kThreads>
 __device__ __forceinline__ void load_rows(const double* __restrict__ xp, long r0, long nrows, int tid,
                                           double (&a2)[TI][D], double (&na)[TI], bool (&live)[TI]) {
 #pragma unroll
@@ -207,12 +207,13 @@ __device__ __forceinline__ void load_rows(const double* __restrict__ xp, long r0
 // ---------------------------------------------------------------------------------------------
 // forward sweep
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int D, int TI, bool SYM>
-__global__ void __launch_bounds__(kThreads, 1) kmv_sweep_kernel(const SweepArgs args) {
+template <int KIND, int D, int TI, bool SYM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) kmv_sweep_kernel(const SweepArgs args) {
     constexpr int DP = SmemLayout<D>::DP;
+    constexpr int kWarps = WARPS, kThreads = WARPS * 32;
     constexpr int BI = kThreads * TI;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileRing<D, 1> ring;
+    TileRing<D, 1, WARPS> ring;
     ring.s_x = reinterpret_cast<double*>(smem_raw);                       // [kStages][kBJ*DP]
     ring.s_v = ring.s_x + kStages * kBJ * DP;                             // [kStages][kBJ]
     double* s_col = ring.s_v + kStages * kBJ;                             // [2][kWarps][kBJ]
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) kmv_sweep_kernel(const SweepArgs 
         const long r0 = cc.I * BI;
         double a2[TI][D], na[TI], vi[TI], racc[TI];
         bool live[TI];
-        load_rows<D, DP, TI>(args.xp_rows, r0, args.nrows, tid, a2, na, live);
+        load_rows<D, DP, TI, kThreads>(args.xp_rows, r0, args.nrows, tid, a2, na, live);
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti) {
             // SYM: rows and columns share the padded vector
@@ -322,12 +323,13 @@ __global__ void __launch_bounds__(kThreads, 1) kmv_sweep_kernel(const SweepArgs 
 //   gvar  += kappa * omega
 // diagonal items visit ordered pairs with u_i,w_i halved and double their row sums at the end.
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int D, int TI>
-__global__ void __launch_bounds__(kThreads, 1) kmv_bwd_kernel(const SweepArgs args) {
+template <int KIND, int D, int TI, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) kmv_bwd_kernel(const SweepArgs args) {
     constexpr int DP = SmemLayout<D>::DP;
+    constexpr int kWarps = WARPS, kThreads = WARPS * 32;
     constexpr int BI = kThreads * TI;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileRing<D, 2> ring;
+    TileRing<D, 2, WARPS> ring;
     ring.s_x = reinterpret_cast<double*>(smem_raw);                       // [kStages][kBJ*DP]
     ring.s_v = ring.s_x + kStages * kBJ * DP;                             // [kStages][2][kBJ]  (w, u)
     double* s_col = ring.s_v + kStages * 2 * kBJ;                         // [2][kWarps][kBJ]
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) kmv_bwd_kernel(const SweepArgs ar
         const long r0 = cc.I * BI;
         double a2[TI][D], na[TI], ui[TI], wi[TI], racc[TI];
         bool live[TI];
-        load_rows<D, DP, TI>(args.xp_rows, r0, args.nrows, tid, a2, na, live);
+        load_rows<D, DP, TI, kThreads>(args.xp_rows, r0, args.nrows, tid, a2, na, live);
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti) {
             const long row = r0 + ti * kThreads + tid;
@@ -634,87 +636,109 @@ static int run_knm(Context* ctx, int bwd, const KnmArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // per-dimension launchers (one translation unit per D, see kmv_inst.cu)
 // ---------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int WARPS>
 static size_t fwd_smem_bytes() {
     constexpr int DP = SmemLayout<D>::DP;
-    return (size_t)(kStages * kBJ * DP + kStages * kBJ + 2 * kWarps * kBJ + 64) * sizeof(double) +
-           2 * kStages * sizeof(uint64_t);
+    return (size_t)(kStages * kBJ * DP + kStages * kBJ + 2 * WARPS * kBJ + 64) * sizeof(double) + 2 * kStages * sizeof(uint64_t);
 }
-template <int D>
+template <int D, int WARPS>
 static size_t bwd_smem_bytes() {
     constexpr int DP = SmemLayout<D>::DP;
-    return (size_t)(kStages * kBJ * DP + kStages * 2 * kBJ + 2 * kWarps * kBJ + 64 + kWarps * (D + 2)) *
-               sizeof(double) +
+    return (size_t)(kStages * kBJ * DP + kStages * 2 * kBJ + 2 * WARPS * kBJ + 64 + WARPS * (D + 2)) * sizeof(double) +
            2 * kStages * sizeof(uint64_t);
 }
 
-template <int KIND, int D, int TI, bool SYM>
+template <int KIND, int D, int TI, bool SYM, int WARPS>
 static int launch_fwd(Context* ctx, SweepArgs a, cudaStream_t st) {
-    constexpr long BI = kThreads * TI;
+    constexpr long BI = WARPS * 32 * TI;
     a.nb_rows = (a.nrows + BI - 1) / BI;
     a.nb_cols = (a.ncols + BI - 1) / BI;
     a.nitems = SYM ? a.nb_rows * (a.nb_rows + 1) / 2 : a.nb_rows * a.nb_cols;
-    auto kern = kmv_sweep_kernel<KIND, D, TI, SYM>;
-    size_t smem = fwd_smem_bytes<D>();
+    auto kern = kmv_sweep_kernel<KIND, D, TI, SYM, WARPS>;
+    size_t smem = fwd_smem_bytes<D, WARPS>();
     CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
     if (my_items <= 0) return CGLB_OK;
     int grid = (int)(my_items < ctx->num_sms ? my_items : ctx->num_sms);
-    kern<<<grid, kThreads, smem, st>>>(a);
+    kern<<<grid, WARPS * 32, smem, st>>>(a);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;
 }
 
-template <int KIND, int D, int TI>
+template <int KIND, int D, int TI, int WARPS>
 static int launch_bwd(Context* ctx, SweepArgs a, cudaStream_t st) {
-    constexpr long BI = kThreads * TI;
+    constexpr long BI = WARPS * 32 * TI;
     a.nb_rows = (a.nrows + BI - 1) / BI;
     a.nb_cols = a.nb_rows;
     a.nitems = a.nb_rows * (a.nb_rows + 1) / 2;
-    auto kern = kmv_bwd_kernel<KIND, D, TI>;
-    size_t smem = bwd_smem_bytes<D>();
+    auto kern = kmv_bwd_kernel<KIND, D, TI, WARPS>;
+    size_t smem = bwd_smem_bytes<D, WARPS>();
     CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
     if (my_items <= 0) return CGLB_OK;
     int grid = (int)(my_items < ctx->num_sms ? my_items : ctx->num_sms);
-    kern<<<grid, kThreads, smem, st>>>(a);
+    kern<<<grid, WARPS * 32, smem, st>>>(a);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;
 }
 
-// Rows per thread: big blocks amortise the column loads best; small problems need more items than SMs.
-static inline int pick_ti(const Context* ctx, long nrows, long ncols, bool sym, int nparts, int max_ti) {
-    for (int ti = max_ti; ti > 1; ti >>= 1) {
-        long bi = (long)kThreads * ti;
-        long nbr = (nrows + bi - 1) / bi, nbc = (ncols + bi - 1) / bi;
-        long items = (sym ? nbr * (nbr + 1) / 2 : nbr * nbc) / nparts;
-        if (items >= 12L * ctx->num_sms) return ti;
-    }
-    return 1;
+// number of work items a (rows-per-CTA) choice yields for this launch
+static inline long count_items(long nrows, long ncols, bool sym, int nparts, long bi) {
+    long nbr = (nrows + bi - 1) / bi, nbc = (ncols + bi - 1) / bi;
+    return (sym ? nbr * (nbr + 1) / 2 : nbr * nbc) / nparts;
 }
 
+#ifdef CGLB_KMV_EXPERIMENT
+// developer build: every (WARPS, TI) variant, selected with the environment variable CGLB_KMV_VARIANT
 template <int KIND, int D, bool SYM>
 static int run_fwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
-    constexpr int MAXTI = SYM ? ((D <= 12) ? 4 : 2) : 2;
-    const int ti = pick_ti(ctx, a.nrows, a.ncols, SYM, a.nparts, MAXTI);
-    if constexpr (MAXTI == 4) {
-        if (ti == 4) return launch_fwd<KIND, D, 4, SYM>(ctx, a, st);
+    const char* e = getenv("CGLB_KMV_VARIANT");
+    int v = e ? atoi(e) : 0;
+    switch (v) {
+        case 84: return launch_fwd<KIND, D, 4, SYM, 8>(ctx, a, st);
+        case 82: return launch_fwd<KIND, D, 2, SYM, 8>(ctx, a, st);
+        case 122: return launch_fwd<KIND, D, 2, SYM, 12>(ctx, a, st);
+        case 123: return launch_fwd<KIND, D, 3, SYM, 12>(ctx, a, st);
+        case 162: return launch_fwd<KIND, D, 2, SYM, 16>(ctx, a, st);
+        case 161: return launch_fwd<KIND, D, 1, SYM, 16>(ctx, a, st);
+        default: return launch_fwd<KIND, D, 4, SYM, 8>(ctx, a, st);
     }
-    if (ti >= 2) return launch_fwd<KIND, D, 2, SYM>(ctx, a, st);
-    return launch_fwd<KIND, D, 1, SYM>(ctx, a, st);
+}
+template <int KIND, int D>
+static int run_bwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
+    const char* e = getenv("CGLB_BWD_VARIANT");
+    int v = e ? atoi(e) : 0;
+    switch (v) {
+        case 82: return launch_bwd<KIND, D, 2, 8>(ctx, a, st);
+        case 81: return launch_bwd<KIND, D, 1, 8>(ctx, a, st);
+        case 122: return launch_bwd<KIND, D, 2, 12>(ctx, a, st);
+        case 121: return launch_bwd<KIND, D, 1, 12>(ctx, a, st);
+        case 161: return launch_bwd<KIND, D, 1, 16>(ctx, a, st);
+        default: return launch_bwd<KIND, D, 2, 8>(ctx, a, st);
+    }
+}
+#else
+// Rows per CTA: big blocks amortise the column loads best; small problems need more items than SMs.
+template <int KIND, int D, bool SYM>
+static int run_fwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
+    constexpr bool BIG = SYM && (D <= 12);
+    if constexpr (BIG) {
+        if (count_items(a.nrows, a.ncols, SYM, a.nparts, 8 * 32 * 4) >= 12L * ctx->num_sms) return launch_fwd<KIND, D, 4, SYM, 8>(ctx, a, st);
+    }
+    if (count_items(a.nrows, a.ncols, SYM, a.nparts, 8 * 32 * 2) >= 12L * ctx->num_sms) return launch_fwd<KIND, D, 2, SYM, 8>(ctx, a, st);
+    return launch_fwd<KIND, D, 1, SYM, 8>(ctx, a, st);
 }
 
 template <int KIND, int D>
 static int run_bwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
-    constexpr int MAXTI = (D <= 12) ? 2 : 1;
-    const int ti = pick_ti(ctx, a.nrows, a.ncols, true, a.nparts, MAXTI);
-    if constexpr (MAXTI == 2) {
-        if (ti == 2) return launch_bwd<KIND, D, 2>(ctx, a, st);
+    if constexpr (D <= 12) {
+        if (count_items(a.nrows, a.ncols, true, a.nparts, 8 * 32 * 2) >= 12L * ctx->num_sms) return launch_bwd<KIND, D, 2, 8>(ctx, a, st);
     }
-    return launch_bwd<KIND, D, 1>(ctx, a, st);
+    return launch_bwd<KIND, D, 1, 8>(ctx, a, st);
 }
+#endif
 
 // dispatch table filled by the per-D translation units
 typedef int (*sweep_fn)(Context*, int kind, int mode /*0 sym fwd, 1 rect fwd, 2 sym bwd*/, const SweepArgs&, cudaStream_t);

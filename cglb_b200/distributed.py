@@ -60,6 +60,11 @@ class Shard:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return t
 
+    def broadcast(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:
+        if self.world > 1:
+            dist.broadcast(t, src=src, group=self.group)
+        return t
+
     def barrier(self):
         if self.world > 1:
             dist.barrier(group=self.group)

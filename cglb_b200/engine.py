@@ -54,6 +54,28 @@ class Engine:
         handle = C.c_void_p()
         check(self.lib.cglb_create(C.byref(handle), device_index), "cglb_create")
         self.ctx = handle
+        # optional per-kernel CUDA-event timing (bench.py roofline): name -> list of (start, end) events
+        self.timing = None
+
+    # ---- optional timing of individual entry points (events on the launching stream) ---------------
+    def enable_timing(self, on: bool = True):
+        self.timing = {} if on else None
+
+    def _timed(self, name, fn):
+        if self.timing is None:
+            return fn()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
+        out = fn()
+        e1.record(torch.cuda.current_stream(self.device))
+        self.timing.setdefault(name, []).append((e0, e1))
+        return out
+
+    def timing_summary(self):
+        """name -> (launches, total ms).  Synchronises."""
+        torch.cuda.synchronize(self.device)
+        return {k: (len(v), float(sum(a.elapsed_time(b) for a, b in v))) for k, v in (self.timing or {}).items()}
 
     # ---- bookkeeping ---------------------------------------------------------------------------
     def stream(self):
@@ -96,8 +118,9 @@ class Engine:
         _req(xp, "xp"); _req(v, "v")
         if out is None:
             out = self.empty(n)
-        check(self.lib.cglb_kmv_sym(self.ctx, KIND_IDS[kind], ptr(xp), n, d, ptr(v), ptr(out), float(variance), float(diag),
-                                    int(part), int(nparts), self.stream()), "cglb_kmv_sym")
+        self._timed("kmv_sym", lambda: check(self.lib.cglb_kmv_sym(
+            self.ctx, KIND_IDS[kind], ptr(xp), n, d, ptr(v), ptr(out), float(variance), float(diag), int(part), int(nparts),
+            self.stream()), "cglb_kmv_sym"))
         return out
 
     def kmv_rect(self, kind, xp_rows, nrows, xp_cols, ncols, d, v, variance, out=None) -> Tensor:
@@ -110,8 +133,9 @@ class Engine:
 
     def kmv_bwd_sym(self, kind, xp, n, d, u, w, variance, lengthscale, out, part=0, nparts=1) -> Tensor:
         _req(xp, "xp"); _req(u, "u"); _req(w, "w"); _req(lengthscale, "lengthscale"); _req(out, "out")
-        check(self.lib.cglb_kmv_bwd_sym(self.ctx, KIND_IDS[kind], ptr(xp), n, d, ptr(u), ptr(w), float(variance),
-                                        ptr(lengthscale), ptr(out), int(part), int(nparts), self.stream()), "cglb_kmv_bwd_sym")
+        self._timed("kmv_bwd_sym", lambda: check(self.lib.cglb_kmv_bwd_sym(
+            self.ctx, KIND_IDS[kind], ptr(xp), n, d, ptr(u), ptr(w), float(variance), ptr(lengthscale), ptr(out), int(part),
+            int(nparts), self.stream()), "cglb_kmv_bwd_sym"))
         return out
 
     # ---- K7 -------------------------------------------------------------------------------------------
@@ -149,31 +173,35 @@ class Engine:
 
     def trsm_left_lower(self, l: Tensor, b: Tensor, n: int, alpha: float = 1.0) -> Tensor:
         _req(l, "l"); _req(b, "b")
-        check(self.lib.cglb_trsm_left_lower(self.ctx, ptr(l), l.shape[0], l.stride(0), ptr(b), n, b.stride(0), float(alpha),
-                                            self.stream()), "cglb_trsm_left_lower")
+        self._timed("trsm", lambda: check(self.lib.cglb_trsm_left_lower(
+            self.ctx, ptr(l), l.shape[0], l.stride(0), ptr(b), n, b.stride(0), float(alpha), self.stream()), "cglb_trsm_left_lower"))
         return b
 
     def syrk(self, a: Tensor, m: int, n: int, out: Tensor, accumulate: bool = False) -> Tensor:
         _req(a, "a"); _req(out, "out")
-        check(self.lib.cglb_syrk(self.ctx, ptr(a), m, n, a.stride(0), ptr(out), out.stride(0), int(accumulate), self.stream()), "cglb_syrk")
+        self._timed("syrk", lambda: check(self.lib.cglb_syrk(
+            self.ctx, ptr(a), m, n, a.stride(0), ptr(out), out.stride(0), int(accumulate), self.stream()), "cglb_syrk"))
         return out
 
     def gemm(self, a: Tensor, b: Tensor, out: Tensor, m: int, n: int, k: int, transb: bool = False, alpha: float = 1.0,
              beta: float = 0.0) -> Tensor:
         _req(a, "a"); _req(b, "b"); _req(out, "out")
-        check(self.lib.cglb_gemm(self.ctx, int(transb), m, n, k, float(alpha), ptr(a), a.stride(0), ptr(b), b.stride(0),
-                                 float(beta), ptr(out), out.stride(0), self.stream()), "cglb_gemm")
+        self._timed("gemm", lambda: check(self.lib.cglb_gemm(
+            self.ctx, int(transb), m, n, k, float(alpha), ptr(a), a.stride(0), ptr(b), b.stride(0), float(beta), ptr(out),
+            out.stride(0), self.stream()), "cglb_gemm"))
         return out
 
     # ---- K3 / K4 --------------------------------------------------------------------------------------
     def precond_project(self, a: Tensor, m: int, ncols: int, r: Tensor, q: Tensor) -> Tensor:
-        check(self.lib.cglb_precond_project(self.ctx, ptr(a), m, ncols, a.stride(0), ptr(r), ptr(q), self.stream()), "cglb_precond_project")
+        self._timed("precond_project", lambda: check(self.lib.cglb_precond_project(
+            self.ctx, ptr(a), m, ncols, a.stride(0), ptr(r), ptr(q), self.stream()), "cglb_precond_project"))
         return q
 
     def precond_finish(self, a: Tensor, m: int, ncols: int, lbinv: Tensor, q: Tensor, r: Tensor, sigma_sq: float,
                        z: Tensor, w: Tensor, rz: Tensor):
-        check(self.lib.cglb_precond_finish(self.ctx, ptr(a), m, ncols, a.stride(0), ptr(lbinv), ptr(q), ptr(r), float(sigma_sq),
-                                           ptr(z), ptr(w), ptr(rz), self.stream()), "cglb_precond_finish")
+        self._timed("precond_finish", lambda: check(self.lib.cglb_precond_finish(
+            self.ctx, ptr(a), m, ncols, a.stride(0), ptr(lbinv), ptr(q), ptr(r), float(sigma_sq), ptr(z), ptr(w), ptr(rz),
+            self.stream()), "cglb_precond_finish"))
 
     # ---- K8 -------------------------------------------------------------------------------------------
     def dot(self, x: Tensor, y: Tensor, out: Tensor) -> Tensor:

@@ -178,12 +178,17 @@ class LowerBoundCG(nn.Module):
     # ---- evaluation -------------------------------------------------------------------------------------
     def evaluator(self, data) -> BoundEvaluator:
         x, y = data
-        key = (x.data_ptr(), y.data_ptr(), tuple(x.shape), x._version, y._version)
+        key = (x.data_ptr(), y.data_ptr(), tuple(x.shape))
+        version = (x._version, y._version)
         if self._evaluator is None or self._evaluator_key != key:
             if not x.is_cuda:
                 raise CglbError("LowerBoundCG needs CUDA tensors: cglb_b200 has no CPU fallback")
             self._evaluator = BoundEvaluator(x.to(torch.float64), y.to(torch.float64), self._shard)
-            self._evaluator_key = key
+            self._evaluator_key, self._evaluator_version = key, version
+        elif self._evaluator_version != version:
+            # same buffers, new contents (e.g. a fresh host->device copy): keep the workspaces
+            self._evaluator.refresh_data(x.to(torch.float64), y.to(torch.float64))
+            self._evaluator_version = version
         return self._evaluator
 
     def _evaluate(self, data, need_grad: bool):

@@ -1,0 +1,78 @@
+"""GPU (-m gpu), >= 2 GPUs: the row-sharded path (NCCL all-reduce of the partial K v, of A r and of (z, rz))
+gives the same bound, gradients and CG iteration count as the oracle.  Skipped on a 1-GPU box."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+CASE = dict(kind="matern32", n=5000, d=3, M=96, noise=0.05, variance=1.2, ls=[0.8, 1.0, 1.3], mean_c=0.1)
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import cglb_b200 as cb
+        from helpers import make_model
+        from oracle import cglb_oracle as o
+        c = CASE
+        x, y, z = o.synthetic_problem(c["n"], c["d"], c["M"], seed=12)
+        model = make_model(c["kind"], x.numpy(), y.numpy(), z.numpy(), c["noise"], c["variance"], c["ls"], c["mean_c"],
+                           device=f"cuda:{rank}")
+        lb = cb.LowerBoundCG(model, shard=cb.Shard.from_env())
+        out = []
+        for mult in (1.0, 1.02):
+            model.covar_module.base_kernel.base_kernel.lengthscale = torch.as_tensor(np.asarray(c["ls"]) * mult)
+            loss = -lb((model.train_inputs[0], model.train_targets))
+            grads = torch.autograd.grad(loss, list(model.parameters()))
+            out.append((float(loss), [g.cpu().numpy() for g in grads], int(model.cg_stats.steps)))
+        pred = cb.PredictCG(model, shard=cb.Shard.from_env())
+        xnew = torch.randn(50, c["d"], dtype=torch.float64, generator=torch.Generator().manual_seed(3)).cuda()
+        fm, fv = pred(xnew)
+        # every rank must hold bit-identical results (all ranks take the same CG / L-BFGS branches)
+        gsum = sum(float(np.abs(g).sum()) for g in out[1][1])
+        t = torch.tensor([out[0][0], out[1][0], gsum], dtype=torch.float64, device=f"cuda:{rank}")
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret.put((out, fm.cpu().numpy(), fv.cpu().numpy(), bool(torch.equal(tmax, tmin))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_row_sharded_bound_matches_oracle(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out, fm, fv, identical = ret.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert identical
+    from oracle import cglb_oracle as o
+    c = CASE
+    x, y, z = o.synthetic_problem(c["n"], c["d"], c["M"], seed=12)
+    v = torch.zeros(c["n"], 1, dtype=torch.float64)
+    for (loss, grads, steps), mult in zip(out, (1.0, 1.02)):
+        p = o.OracleParams.from_values(c["noise"], c["mean_c"], z, c["variance"], np.asarray(c["ls"]) * mult)
+        ref_loss, ref_grads, res = o.bound_and_grads(c["kind"], p, x, y, v)
+        v = res.v
+        assert abs(steps - res.cg.steps) <= 1
+        if steps == res.cg.steps:
+            assert abs(loss - float(ref_loss)) <= 1e-7 * abs(float(ref_loss))
+            for a, b in zip(grads, ref_grads):
+                assert np.abs(a - b.numpy()).max() <= 1e-6 * np.abs(b.numpy()).max() + 1e-9
