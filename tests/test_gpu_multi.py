@@ -33,6 +33,13 @@ def _worker(rank, world, port, ret):
             loss = -lb((model.train_inputs[0], model.train_targets))
             grads = torch.autograd.grad(loss, list(model.parameters()))
             out.append((float(loss), [g.cpu().numpy() for g in grads], int(model.cg_stats.steps)))
+        # fixed v (CG disabled): every term is a deterministic function of v -> tight comparison
+        vfix = 0.1 * torch.randn(c["n"], 1, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+        model.v_vec.data.copy_(vfix.cuda())
+        lbf = cb.LowerBoundCG(model, use_cache=True, cached_v_vec_initial=True, shard=cb.Shard.from_env())
+        lossf = -lbf((model.train_inputs[0], model.train_targets))
+        gradsf = torch.autograd.grad(lossf, list(model.parameters()))
+        fixed = (float(lossf), [g.cpu().numpy() for g in gradsf])
         pred = cb.PredictCG(model, shard=cb.Shard.from_env())
         xnew = torch.randn(50, c["d"], dtype=torch.float64, generator=torch.Generator().manual_seed(3)).cuda()
         fm, fv = pred(xnew)
@@ -43,7 +50,7 @@ def _worker(rank, world, port, ret):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         if rank == 0:
-            ret.put((out, fm.cpu().numpy(), fv.cpu().numpy(), bool(torch.equal(tmax, tmin))))
+            ret.put((out, fixed, fm.cpu().numpy(), fv.cpu().numpy(), bool(torch.equal(tmax, tmin))))
     finally:
         dist.destroy_process_group()
 
@@ -58,7 +65,7 @@ def test_row_sharded_bound_matches_oracle(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
-    out, fm, fv, identical = ret.get(timeout=600)
+    out, fixed, fm, fv, identical = ret.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -74,5 +81,12 @@ def test_row_sharded_bound_matches_oracle(world):
         assert abs(steps - res.cg.steps) <= 1
         if steps == res.cg.steps:
             assert abs(loss - float(ref_loss)) <= 1e-7 * abs(float(ref_loss))
-            for a, b in zip(grads, ref_grads):
-                assert np.abs(a - b.numpy()).max() <= 1e-6 * np.abs(b.numpy()).max() + 1e-9
+            # (gradients along a CG trajectory depend on the unconverged residual, which amplifies the
+            #  different summation order of the sharded run; they are compared below at fixed v)
+    vfix = 0.1 * torch.randn(c["n"], 1, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    p = o.OracleParams.from_values(c["noise"], c["mean_c"], z, c["variance"], np.asarray(c["ls"]) * 1.02)
+    res = o.lower_bound(c["kind"], p, x, y, vfix, use_cached_v=True)
+    ref_grads = torch.autograd.grad(-res.bound, p.tensors())
+    assert abs(fixed[0] + float(res.bound)) <= 1e-10 * abs(float(res.bound))
+    for a, b in zip(fixed[1], ref_grads):
+        assert np.abs(a - b.numpy()).max() <= 1e-8 * np.abs(b.numpy()).max() + 1e-10
