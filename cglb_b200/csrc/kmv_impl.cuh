@@ -207,7 +207,9 @@ __device__ __forceinline__ void load_rows(const double* __restrict__ xp, long r0
 // ---------------------------------------------------------------------------------------------
 // forward sweep
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int D, int TI, bool SYM, int WARPS>
+// CB = columns whose pair evaluations are interleaved: CB*TI independent dependency chains per warp (the
+// FP64 pipe needs ~12+ chains per scheduler to hide the 8-cycle DFMA latency through the sqrt/exp chains)
+template <int KIND, int D, int TI, bool SYM, int WARPS, int CB>
 __global__ void __launch_bounds__(WARPS * 32, 1) kmv_sweep_kernel(const SweepArgs args) {
     constexpr int DP = SmemLayout<D>::DP;
     constexpr int kWarps = WARPS, kThreads = WARPS * 32;
@@ -265,28 +267,47 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_sweep_kernel(const SweepArg
             for (int jg = 0; jg < kBJ; jg += kCG) {
                 double c[kCG];
 #pragma unroll
-                for (int jj = 0; jj < kCG; ++jj) {
-                    const double2* bp = reinterpret_cast<const double2*>(sx + (jg + jj) * DP);
-                    double b[DP];
+                for (int jb = 0; jb < kCG; jb += CB) {
+                    double q[CB][TI], vj[CB];
+                    // phase 1: CB*TI squared distances, dimension-major so that the chains interleave
+                    {
+                        double b[CB][DP];
 #pragma unroll
-                    for (int h = 0; h < DP / 2; ++h) {
-                        double2 p = bp[h];
-                        b[2 * h] = p.x;
-                        b[2 * h + 1] = p.y;
+                        for (int cb = 0; cb < CB; ++cb) {
+                            const double2* bp = reinterpret_cast<const double2*>(sx + (jg + jb + cb) * DP);
+#pragma unroll
+                            for (int h = 0; h < DP / 2; ++h) {
+                                double2 p = bp[h];
+                                b[cb][2 * h] = p.x;
+                                b[cb][2 * h + 1] = p.y;
+                            }
+                            vj[cb] = sv[jg + jb + cb];
+#pragma unroll
+                            for (int ti = 0; ti < TI; ++ti) q[cb][ti] = na[ti] + b[cb][DP - 1];
+                        }
+#pragma unroll
+                        for (int k = 0; k < D; ++k)
+#pragma unroll
+                            for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                                for (int ti = 0; ti < TI; ++ti) q[cb][ti] = fma(a2[ti][k], b[cb][k], q[cb][ti]);
                     }
-                    const double nb = b[DP - 1];
-                    const double vj = sv[jg + jj];
-                    double cs = 0.0;
+                    // phase 2: kernel map on all chains
 #pragma unroll
-                    for (int ti = 0; ti < TI; ++ti) {
-                        double q = na[ti] + nb;
+                    for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
-                        for (int k = 0; k < D; ++k) q = fma(a2[ti][k], b[k], q);
-                        const double kk = kappa<KIND>(q, s_tab);
-                        racc[ti] = fma(kk, vj, racc[ti]);
-                        if (SYM) cs = fma(kk, vi[ti], cs);
+                        for (int ti = 0; ti < TI; ++ti) q[cb][ti] = kappa<KIND>(q[cb][ti], s_tab);
+                    // phase 3: row / column accumulation
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) {
+                        double cs = 0.0;
+#pragma unroll
+                        for (int ti = 0; ti < TI; ++ti) {
+                            racc[ti] = fma(q[cb][ti], vj[cb], racc[ti]);
+                            if (SYM) cs = fma(q[cb][ti], vi[ti], cs);
+                        }
+                        c[jb + cb] = cs;
                     }
-                    c[jj] = cs;
                 }
                 if (offdiag) {
                     col_reduce<kCG>(c, lane);
@@ -648,13 +669,13 @@ static size_t bwd_smem_bytes() {
            2 * kStages * sizeof(uint64_t);
 }
 
-template <int KIND, int D, int TI, bool SYM, int WARPS>
+template <int KIND, int D, int TI, bool SYM, int WARPS, int CB>
 static int launch_fwd(Context* ctx, SweepArgs a, cudaStream_t st) {
     constexpr long BI = WARPS * 32 * TI;
     a.nb_rows = (a.nrows + BI - 1) / BI;
     a.nb_cols = (a.ncols + BI - 1) / BI;
     a.nitems = SYM ? a.nb_rows * (a.nb_rows + 1) / 2 : a.nb_rows * a.nb_cols;
-    auto kern = kmv_sweep_kernel<KIND, D, TI, SYM, WARPS>;
+    auto kern = kmv_sweep_kernel<KIND, D, TI, SYM, WARPS, CB>;
     size_t smem = fwd_smem_bytes<D, WARPS>();
     CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
@@ -695,15 +716,18 @@ static inline long count_items(long nrows, long ncols, bool sym, int nparts, lon
 template <int KIND, int D, bool SYM>
 static int run_fwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
     const char* e = getenv("CGLB_KMV_VARIANT");
-    int v = e ? atoi(e) : 0;
+    int v = e ? atoi(e) : 0;      // WARPS*100 + TI*10 + CB
     switch (v) {
-        case 84: return launch_fwd<KIND, D, 4, SYM, 8>(ctx, a, st);
-        case 82: return launch_fwd<KIND, D, 2, SYM, 8>(ctx, a, st);
-        case 122: return launch_fwd<KIND, D, 2, SYM, 12>(ctx, a, st);
-        case 123: return launch_fwd<KIND, D, 3, SYM, 12>(ctx, a, st);
-        case 162: return launch_fwd<KIND, D, 2, SYM, 16>(ctx, a, st);
-        case 161: return launch_fwd<KIND, D, 1, SYM, 16>(ctx, a, st);
-        default: return launch_fwd<KIND, D, 4, SYM, 8>(ctx, a, st);
+        case 841: return launch_fwd<KIND, D, 4, SYM, 8, 1>(ctx, a, st);
+        case 842: return launch_fwd<KIND, D, 4, SYM, 8, 2>(ctx, a, st);
+        case 832: return launch_fwd<KIND, D, 3, SYM, 8, 2>(ctx, a, st);
+        case 824: return launch_fwd<KIND, D, 2, SYM, 8, 4>(ctx, a, st);
+        case 1222: return launch_fwd<KIND, D, 2, SYM, 12, 2>(ctx, a, st);
+        case 1224: return launch_fwd<KIND, D, 2, SYM, 12, 4>(ctx, a, st);
+        case 1232: return launch_fwd<KIND, D, 3, SYM, 12, 2>(ctx, a, st);
+        case 1622: return launch_fwd<KIND, D, 2, SYM, 16, 2>(ctx, a, st);
+        case 1614: return launch_fwd<KIND, D, 1, SYM, 16, 4>(ctx, a, st);
+        default: return launch_fwd<KIND, D, 4, SYM, 8, 1>(ctx, a, st);
     }
 }
 template <int KIND, int D>
@@ -725,10 +749,10 @@ template <int KIND, int D, bool SYM>
 static int run_fwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
     constexpr bool BIG = SYM && (D <= 12);
     if constexpr (BIG) {
-        if (count_items(a.nrows, a.ncols, SYM, a.nparts, 8 * 32 * 4) >= 12L * ctx->num_sms) return launch_fwd<KIND, D, 4, SYM, 8>(ctx, a, st);
+        if (count_items(a.nrows, a.ncols, SYM, a.nparts, 8 * 32 * 4) >= 12L * ctx->num_sms) return launch_fwd<KIND, D, 4, SYM, 8, 1>(ctx, a, st);
     }
-    if (count_items(a.nrows, a.ncols, SYM, a.nparts, 8 * 32 * 2) >= 12L * ctx->num_sms) return launch_fwd<KIND, D, 2, SYM, 8>(ctx, a, st);
-    return launch_fwd<KIND, D, 1, SYM, 8>(ctx, a, st);
+    if (count_items(a.nrows, a.ncols, SYM, a.nparts, 8 * 32 * 2) >= 12L * ctx->num_sms) return launch_fwd<KIND, D, 2, SYM, 8, 2>(ctx, a, st);
+    return launch_fwd<KIND, D, 1, SYM, 8, 4>(ctx, a, st);
 }
 
 template <int KIND, int D>

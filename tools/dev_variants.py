@@ -12,21 +12,21 @@ def timeit(fn, reps=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 res = {}
-for kind, n, d in [("matern32", 200000, 11), ("matern32", 300000, 3), ("rbf", 40000, 8), ("rbf", 200000, 8)]:
+for kind, n, d in [("matern32", 200000, 11), ("matern32", 300000, 3), ("rbf", 200000, 8)]:
     g = torch.Generator(device=dev).manual_seed(0)
     x = torch.randn(n, d, generator=g, dtype=torch.float64, device=dev)
     v = torch.randn(n, generator=g, dtype=torch.float64, device=dev); u = torch.randn(n, generator=g, dtype=torch.float64, device=dev)
     ls = torch.full((d,), 0.5 * d ** 0.5, dtype=torch.float64, device=dev)
     xp = eng.pack(kind, x, ls, x.mean(0)); y = eng.empty(n); out = eng.zeros(d + 1)
     ref = None
-    for var in ["84", "82", "122", "123", "162", "161"]:
+    for var in ["841", "842", "832", "824", "1222", "1224", "1232", "1622", "1614"]:
         os.environ["CGLB_KMV_VARIANT"] = var
         ms = timeit(lambda: eng.kmv_sym(kind, xp, n, d, v, 1.0, 0.01, out=y))
         if ref is None: ref = y.clone()
         err = float((y - ref).norm() / ref.norm())
         print(f"fwd {kind} n={n} d={d} variant {var}: {ms:8.3f} ms  {n*n/ms/1e6:8.1f} Gpairs/s  relerr_vs_first {err:.1e}", flush=True)
         res[f"fwd_{kind}_{n}_{d}_{var}"] = n * n / ms / 1e6
-    for var in ["82", "81", "122", "121", "161"]:
+    for var in []:
         os.environ["CGLB_BWD_VARIANT"] = var
         ms = timeit(lambda: eng.kmv_bwd_sym(kind, xp, n, d, u, v, 1.0, ls, out))
         print(f"bwd {kind} n={n} d={d} variant {var}: {ms:8.3f} ms  {n*n/ms/1e6:8.1f} Gpairs/s", flush=True)

@@ -1,0 +1,97 @@
+// Upper bound of the sweep's inner body: register-resident rows, synthetic columns (no memory traffic except
+// the exp table in shared memory).  Reports pair evaluations/s and FP64 slots/s for a few launch shapes.
+#include <cstdio>
+#include "../cglb_b200/csrc/kmv_impl.cuh"
+using namespace cglb;
+namespace cglb { void set_error(const char*, ...) {} int ensure_vpad(Context*, long) { return 0; } int ensure_scratch(Context*, long) { return 0; }
+sweep_fn get_sweep_fn(int) { return nullptr; } knm_fn get_knm_fn(int) { return nullptr; } }
+
+template <int KIND, int D, int TI, int MODE>
+__global__ void __launch_bounds__(256) body(double* out, const double* tabg, int iters, double seed) {
+    __shared__ double s_tab[64];
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = tabg[threadIdx.x];
+    __syncthreads();
+    double a2[TI][D], na[TI], racc[TI];
+#pragma unroll
+    for (int ti = 0; ti < TI; ++ti) {
+        na[ti] = 1.0 + ti + seed;
+        racc[ti] = 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) a2[ti][k] = -2.0 * (0.01 * (k + 1) + 1e-3 * threadIdx.x + ti * 0.1);
+    }
+    double b[D], nb = 1.3 + seed, vj = 0.7;
+#pragma unroll
+    for (int k = 0; k < D; ++k) b[k] = 0.02 * k + seed;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+            for (int ti = 0; ti < TI; ++ti) {
+                double q = na[ti] + nb;
+#pragma unroll
+                for (int k = 0; k < D; ++k) q = fma(a2[ti][k], b[k], q);
+                double kk;
+                if (MODE == 0) kk = kappa<KIND>(q, s_tab);           // full map
+                else if (MODE == 1) kk = q;                            // distance only
+                else if (MODE == 2) { q = clamp_sq_t<0x42F00000>(q); kk = fast_sqrt(q); }   // distance + sqrt
+                else {
+                    // exp variants on s = q (clamped): 3 = polynomial only (no table, no scaling), 4 = + table lookup,
+                    // 5 = + exponent scaling but table constant, 6 = n via cvt instead of magic add
+                    q = clamp_sq_t<0x41700000>(q);
+                    const double MAGIC = 6755399441055744.0, C = 92.332482616893656820, L = 1.0830424696249145255e-02;
+                    double t = fma(q, -C, MAGIC);
+                    int n = __double2loint(t);
+                    double nf = t - MAGIC;
+                    double r = fma(nf, -L, -q);
+                    double p = fma(r, 8.3333333333333332177e-03, 4.1666666666666664354e-02);
+                    p = fma(p, r, 1.6666666666666665741e-01); p = fma(p, r, 0.5); p = fma(p, r, 1.0);
+                    double T = (MODE == 4 || MODE == 6) ? s_tab[n & 63] : 1.25;
+                    double Tr = T * r;
+                    double res = fma(Tr, p, T);
+                    if (MODE == 5 || MODE == 6) res = __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+                    kk = res;
+                }
+                racc[ti] = fma(kk, vj, racc[ti]);
+            }
+            nb += 1e-7; b[jj % D] += 1e-7;      // keep the compiler from hoisting
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int ti = 0; ti < TI; ++ti) s += racc[ti];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int KIND, int D, int TI, int MODE>
+void run(const char* name, double* out, double* tab, int sms, double slots) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int iters = 4000;
+    for (int bps = 2; bps <= 2; ++bps) {
+        int blocks = sms * bps;
+        body<KIND, D, TI, MODE><<<blocks, 256>>>(out, tab, 10, 0.0); cudaDeviceSynchronize();
+        cudaEventRecord(e0); body<KIND, D, TI, MODE><<<blocks, 256>>>(out, tab, iters, 0.0); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double pairs = (double)iters * 8 * TI * blocks * 256;
+        printf("%-28s TI=%d blocks/SM=%d: %8.1f Gpairs/s  fp64 slots %.1f/pair -> pipe %.1f%% of 64 lanes/clk/SM @1965MHz\n", name, TI, bps,
+               pairs / (ms * 1e-3) / 1e9, slots, 100.0 * pairs * slots / (ms * 1e-3) / (sms * 64.0 * 1.965e9));
+    }
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0); int sms = p.multiProcessorCount;
+    double* out; cudaMalloc(&out, sizeof(double) * sms * 2 * 256);
+    double tab[64], *dtab; for (int j = 0; j < 64; ++j) tab[j] = exp2(j / 64.0);
+    cudaMalloc(&dtab, sizeof(tab)); cudaMemcpy(dtab, tab, sizeof(tab), cudaMemcpyHostToDevice);
+    run<CGLB_MATERN32, 11, 4, 0>("matern32 d=11 full", out, dtab, sms, 28);
+    run<CGLB_MATERN32, 11, 2, 0>("matern32 d=11 full", out, dtab, sms, 28);
+    run<CGLB_MATERN32, 11, 4, 1>("d=11 distance only", out, dtab, sms, 13);
+    run<CGLB_MATERN32, 11, 4, 2>("d=11 distance+sqrt", out, dtab, sms, 18);
+    run<CGLB_RBF, 11, 4, 0>("rbf d=11 full", out, dtab, sms, 22);
+    run<CGLB_RBF, 11, 4, 3>("d=11 dist+exp poly only", out, dtab, sms, 22);
+    run<CGLB_RBF, 11, 4, 4>("d=11 dist+exp poly+table", out, dtab, sms, 22);
+    run<CGLB_RBF, 11, 4, 5>("d=11 dist+exp poly+scale", out, dtab, sms, 22);
+    run<CGLB_RBF, 11, 4, 6>("d=11 dist+exp table+scale", out, dtab, sms, 22);
+    run<CGLB_MATERN32, 3, 4, 0>("matern32 d=3 full", out, dtab, sms, 20);
+    run<CGLB_MATERN32, 3, 8, 0>("matern32 d=3 full", out, dtab, sms, 20);
+    return 0;
+}
