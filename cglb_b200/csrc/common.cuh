@@ -68,7 +68,17 @@ int ensure_scratch(Context* ctx, long n_doubles);
 //   multiple of 16 bytes (TMA bulk copies and LDS.128 broadcasts need that).
 //   Rows are padded to a multiple of CGLB_ROW_PAD with zeros.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline int packed_width(int d) { return (d + 2) & ~1; }
+//   d > CGLB_MAX_REGISTER_D ("wide" layout for the DMMA sweeps): coordinates zero-padded to KP = d rounded up
+//   to a multiple of 4, |a|^2 at index KP, row width W = KP + 4 or KP + 8 chosen so that W mod 16 is 4 or 12
+//   (conflict-free DMMA fragment loads straight from the TMA-landed tile).
+#define CGLB_MAX_REGISTER_D 32
+__host__ __device__ inline int wide_kp(int d) { return (d + 3) & ~3; }
+__host__ __device__ inline int packed_width(int d) {
+    if (d <= CGLB_MAX_REGISTER_D) return (d + 2) & ~1;
+    const int kp = wide_kp(d);
+    return kp + ((kp % 8 == 0) ? 4 : 8);
+}
+__host__ __device__ inline int norm_index(int d) { return d <= CGLB_MAX_REGISTER_D ? packed_width(d) - 1 : wide_kp(d); }
 __host__ __device__ inline long padded_rows(long n) { return (n + CGLB_ROW_PAD - 1) / CGLB_ROW_PAD * CGLB_ROW_PAD; }
 
 // ---------------------------------------------------------------------------------------------

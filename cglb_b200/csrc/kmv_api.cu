@@ -20,8 +20,8 @@ __global__ void pack_inputs_kernel(int kind, const double* __restrict__ x, long 
         o[k] = a;
         nrm = fma(a, a, nrm);
     }
-    for (int k = d; k < dp - 1; ++k) o[k] = 0.0;
-    o[dp - 1] = nrm;
+    for (int k = d; k < dp; ++k) o[k] = 0.0;
+    o[norm_index(d)] = nrm;
 }
 
 // vpad = [v, 0...]; y = diag * v (or 0)
@@ -104,7 +104,12 @@ sweep_fn get_sweep_fn(int d) {
     }
 }
 
+int wide_sweep(Context* ctx, int kind, bool sym, const double* xp_rows, long nrows, const double* xp_cols, long ncols, int d,
+               const double* vcol, double* y, double variance, int part, int nparts, cudaStream_t st);
+
 static int dispatch(Context* ctx, int kind, int d, int mode, const SweepArgs& a, cudaStream_t st) {
+    if (d > CGLB_MAX_REGISTER_D && mode != 2)
+        return wide_sweep(ctx, kind, mode == 0, a.xp_rows, a.nrows, a.xp_cols, a.ncols, d, a.vcol, a.y, a.variance, a.part, a.nparts, st);
     sweep_fn f = get_sweep_fn(d);
     if (!f) {
         set_error("kernel sweep: d=%d has no register-resident instantiation in this build", d);

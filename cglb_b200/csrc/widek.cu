@@ -1,0 +1,265 @@
+// Wide-input (d > 32, e.g. the song-shaped d = 90 config) matrix-free sweeps: the distance contraction
+// a_i . b_j runs on DMMA.8x8x4 with both operand tiles in shared memory; the kernel map, the products with
+// v and the row/column reductions are applied to the accumulator fragments in registers.
+//
+//   CTA = 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 32 pairs = 4 x 4 DMMA tiles
+//   work item = (row block of 128 rows, chunk of 1024 columns) ; the row tile stays resident, 64-column
+//   tiles stream through a 2-stage TMA (cp.async.bulk) ring; symmetric sweep: tiles on/above the diagonal
+//   only, off-diagonal tiles feed y_i and y_j.
+// Algorithmic FLOPs per pair (expanded form): 2d + 10 (Matern32).
+#include "kmv_impl.cuh"
+
+namespace cglb {
+
+constexpr int WT_ROWS = 128;         // rows per item
+constexpr int WT_COLS = 64;          // columns per streamed tile
+constexpr int WT_CHUNK = 1024;       // columns per item
+constexpr int WT_THREADS = 256;
+
+struct WideArgs {
+    const double* xp_rows; const double* xp_cols;   // wide packed [.][W]
+    const double* vcol;                              // padded column vector
+    double* y;
+    const double* exp_tab;
+    long nrows, ncols;
+    long nb_rows;            // row blocks of 128
+    long n_chunks;           // column chunks of 1024
+    long nitems;
+    double variance;
+    int d, kp, w;
+    int part, nparts;
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// item t -> (row block I, column chunk c).  SYM: chunk-major enumeration of {(I, c) : I < 8 (c + 1)} (the
+// row block must start at or before the end of the chunk); entries with I >= nb_rows are skipped.
+__device__ __forceinline__ bool wide_item(long t, const WideArgs& a, bool sym, long& I, long& c) {
+    if (!sym) { I = t / a.n_chunks; c = t % a.n_chunks; return true; }
+    long cc = (long)((sqrt(1.0 + (double)t) - 1.0) * 0.5);
+    while (4 * cc * (cc + 1) > t) --cc;
+    while (4 * (cc + 1) * (cc + 2) <= t) ++cc;
+    c = cc;
+    I = t - 4 * cc * (cc + 1);
+    return I < a.nb_rows;
+}
+
+template <int KIND, bool SYM>
+__global__ void __launch_bounds__(WT_THREADS, 1) wide_sweep_kernel(const WideArgs args) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = args.w, KP = args.kp;
+    double* s_rows = reinterpret_cast<double*>(smem_raw);                 // [128][W]
+    double* s_cols = s_rows + WT_ROWS * W;                                // [2][64][W]
+    double* s_v = s_cols + 2 * WT_COLS * W;                               // [2][64]
+    double* s_col = s_v + 2 * WT_COLS;                                    // [2][4][64] per row-warp column sums, by tile parity
+    double* s_row = s_col + 8 * WT_COLS;                                  // [2][128]  per col-warp row sums
+    double* s_tab = s_row + 2 * WT_ROWS;                                  // [64]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_tab + 64);           // [2] column tiles
+    uint64_t* s_empty = s_full + 2;                                       // [2]
+    uint64_t* s_rowbar = s_empty + 2;                                     // [1] row tile
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    if (tid < 64) s_tab[tid] = args.exp_tab[tid];
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], 8); mbar_init(&s_empty[1], 8);
+        mbar_init(s_rowbar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    int stage = 0; uint32_t phase = 0;          // consumer side of the column ring
+    int pstage = 0; uint32_t pphase = 0;        // producer side
+    uint32_t rowphase = 0;
+    const double var = args.variance;
+    const uint32_t tile_bytes = (uint32_t)(WT_COLS * W * sizeof(double));
+
+    for (long tau = blockIdx.x;; tau += gridDim.x) {
+        const long t = tau * args.nparts + args.part;
+        if (t >= args.nitems) break;
+        long I, C;
+        if (!wide_item(t, args, SYM, I, C)) continue;
+        const long r0 = I * WT_ROWS;
+        const long cbeg0 = C * WT_CHUNK;
+        long cend = cbeg0 + WT_CHUNK;
+        if (cend > args.ncols) cend = args.ncols;
+        // SYM: first tile at or after the start of the row block (tiles are 64 wide, the row block 128)
+        long cbeg = cbeg0;
+        if (SYM && cbeg < r0) cbeg = r0;
+        if (cbeg >= cend) continue;
+        const int ntiles = (int)((cend - cbeg + WT_COLS - 1) / WT_COLS);
+
+        // all warps are done with the previous item's row tile before it is overwritten
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(s_rowbar, (uint32_t)(WT_ROWS * W * sizeof(double)));
+            tma_load_1d(s_rows, args.xp_rows + r0 * W, (uint32_t)(WT_ROWS * W * sizeof(double)), s_rowbar);
+            // first column tile
+            mbar_wait(&s_empty[pstage], pphase ^ 1);
+            mbar_expect_tx(&s_full[pstage], tile_bytes + WT_COLS * sizeof(double));
+            tma_load_1d(s_cols + pstage * WT_COLS * W, args.xp_cols + cbeg * W, tile_bytes, &s_full[pstage]);
+            tma_load_1d(s_v + pstage * WT_COLS, args.vcol + cbeg, WT_COLS * sizeof(double), &s_full[pstage]);
+            if (++pstage == 2) { pstage = 0; pphase ^= 1; }
+        }
+        mbar_wait(s_rowbar, rowphase);
+        rowphase ^= 1;
+
+        double na[4], vrow[4], racc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = wm * 32 + i * 8 + g;
+            na[i] = s_rows[r * W + KP];
+            const long row = r0 + r;
+            vrow[i] = (SYM && row < args.nrows) ? __ldg(args.vcol + row) : 0.0;
+            racc[i] = 0.0;
+        }
+
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const long j0 = cbeg + (long)tile * WT_COLS;
+            if (tid == 0 && tile + 1 < ntiles) {                 // prefetch the next column tile
+                mbar_wait(&s_empty[pstage], pphase ^ 1);
+                mbar_expect_tx(&s_full[pstage], tile_bytes + WT_COLS * sizeof(double));
+                tma_load_1d(s_cols + pstage * WT_COLS * W, args.xp_cols + (j0 + WT_COLS) * W, tile_bytes, &s_full[pstage]);
+                tma_load_1d(s_v + pstage * WT_COLS, args.vcol + j0 + WT_COLS, WT_COLS * sizeof(double), &s_full[pstage]);
+                if (++pstage == 2) { pstage = 0; pphase ^= 1; }
+            }
+            __syncwarp();
+            mbar_wait(&s_full[stage], phase);
+            const double* sc = s_cols + stage * WT_COLS * W;
+            const double* sv = s_v + stage * WT_COLS;
+            // SYM: a tile that overlaps the diagonal block of this row block contributes to rows only
+            const bool offdiag = SYM && (j0 >= r0 + WT_ROWS);
+
+            double acc[4][4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            const double* ap = s_rows + (wm * 32 + g) * W + t4;
+            const double* bp = sc + (wn * 32 + g) * W + t4;
+#pragma unroll 2
+            for (int k4 = 0; k4 < KP; k4 += 4) {
+                double af[4], bf[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) af[i] = ap[i * 8 * W + k4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = bp[j * 8 * W + k4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j], af[i], bf[j]);
+            }
+            // epilogue on the fragments: lane holds (row g + 8i, cols 8j + 2 t4 + e)
+            double cacc[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double nb[2], vc[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = wn * 32 + j * 8 + 2 * t4 + e;
+                    nb[e] = sc[c * W + KP];
+                    vc[e] = sv[c];
+                    cacc[j][e] = 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double q = fma(-2.0, acc[i][j][e], na[i] + nb[e]);
+                        const double kk = kappa<KIND>(q, s_tab);
+                        racc[i] = fma(kk, vc[e], racc[i]);
+                        if (SYM) cacc[j][e] = fma(kk, vrow[i], cacc[j][e]);
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stage]);
+            if (++stage == 2) { stage = 0; phase ^= 1; }
+
+            if (offdiag) {
+                // reduce the 8 column partials over the 8 lanes that share t4 (bits 2..4 of the lane id):
+                // transposing butterfly, 7 adds instead of 24
+                double c8[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { c8[2 * j] = cacc[j][0]; c8[2 * j + 1] = cacc[j][1]; }
+                int cnt = 8;
+#pragma unroll
+                for (int off = 16; off >= 4; off >>= 1, cnt >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int h = 0; h < cnt / 2; ++h) {
+                        const double send = up ? c8[h] : c8[h + cnt / 2];
+                        const double keep = up ? c8[h + cnt / 2] : c8[h];
+                        c8[h] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                // lane now holds entry idx = (bit4, bit3, bit2) of c8 order: idx = 2 j + e
+                const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                const int col = wn * 32 + (idx >> 1) * 8 + 2 * t4 + (idx & 1);
+                s_col[((tile & 1) * 4 + wm) * WT_COLS + col] = c8[0];
+            }
+            if (SYM) {
+                __syncthreads();          // also orders s_col reuse between tiles
+                if (offdiag && tid < WT_COLS) {
+                    const long j = j0 + tid;
+                    const double* sc4 = s_col + (tile & 1) * 4 * WT_COLS;
+                    const double s = sc4[tid] + sc4[WT_COLS + tid] + sc4[2 * WT_COLS + tid] + sc4[3 * WT_COLS + tid];
+                    if (j < args.ncols) atomicAdd(args.y + j, var * s);
+                }
+            }
+        }
+        // row sums: reduce over the 4 lanes sharing g, then over the 2 column warps
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double s = racc[i];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (t4 == 0) s_row[wn * WT_ROWS + wm * 32 + i * 8 + g] = s;
+        }
+        __syncthreads();
+        if (tid < WT_ROWS) {
+            const long row = r0 + tid;
+            if (row < args.nrows) atomicAdd(args.y + row, var * (s_row[tid] + s_row[WT_ROWS + tid]));
+        }
+    }
+}
+
+static size_t wide_smem_bytes(int w) {
+    return (size_t)(WT_ROWS * w + 2 * WT_COLS * w + 2 * WT_COLS + 8 * WT_COLS + 2 * WT_ROWS + 64) * sizeof(double) + 8 * sizeof(uint64_t);
+}
+
+int wide_sweep(Context* ctx, int kind, bool sym, const double* xp_rows, long nrows, const double* xp_cols, long ncols, int d,
+               const double* vcol, double* y, double variance, int part, int nparts, cudaStream_t st) {
+    WideArgs a{};
+    a.xp_rows = xp_rows; a.xp_cols = xp_cols; a.vcol = vcol; a.y = y; a.exp_tab = ctx->exp_table;
+    a.nrows = nrows; a.ncols = ncols; a.variance = variance; a.d = d; a.kp = wide_kp(d); a.w = packed_width(d);
+    a.part = part; a.nparts = nparts;
+    a.nb_rows = (nrows + WT_ROWS - 1) / WT_ROWS;
+    a.n_chunks = (ncols + WT_CHUNK - 1) / WT_CHUNK;
+    a.nitems = sym ? 4 * a.n_chunks * (a.n_chunks + 1) : a.nb_rows * a.n_chunks;
+    size_t smem = wide_smem_bytes(a.w);
+    if (smem > 227 * 1024) {
+        set_error("wide sweep: d=%d needs %zu bytes of shared memory (> 227 KB); d <= 104 is supported", d, smem);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    long my_items = (a.nitems - part + nparts - 1) / nparts;
+    if (my_items <= 0) return CGLB_OK;
+    int grid = (int)(my_items < ctx->num_sms ? my_items : ctx->num_sms);
+#define LAUNCH(K, S)                                                                                             \
+    do {                                                                                                         \
+        CGLB_CUDA_OK(cudaFuncSetAttribute(wide_sweep_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        wide_sweep_kernel<K, S><<<grid, WT_THREADS, smem, st>>>(a);                                               \
+    } while (0)
+    if (kind == CGLB_MATERN32) { if (sym) LAUNCH(CGLB_MATERN32, true); else LAUNCH(CGLB_MATERN32, false); }
+    else { if (sym) LAUNCH(CGLB_RBF, true); else LAUNCH(CGLB_RBF, false); }
+#undef LAUNCH
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+}  // namespace cglb
