@@ -36,6 +36,7 @@ WORKLOADS = {
     "snelson1d": ("snelson1d-shaped synthetic 1-D n=2000 Matern32 M=1024 fp64", "matern32", 2000, 1, 1024),
     "kin40k": ("kin40k-shaped synthetic n=40k d=8 RBF M=1024 fp64", "rbf", 40000, 8, 1024),
     "3droad": ("3droad-shaped synthetic n=434k d=3 Matern32 M=2048 fp64", "matern32", 434000, 3, 2048),
+    "song": ("song-shaped synthetic n=515k d=90 Matern32 M=2048 fp64 (DMMA distance contraction)", "matern32", 515000, 90, 2048),
     "houseelectric": ("houseelectric-shaped synthetic n=2M d=11 Matern32 M=2048 fp64", "matern32", 2000000, 11, 2048),
 }
 DEFAULT_WORKLOAD = "houseelectric"          # the configuration BASELINE.json's metric is quoted on (n = 2M); fits one B200
@@ -47,7 +48,10 @@ LS_MULTS = (1.0, 1.01, 0.99)
 
 
 def algorithmic_flops_per_pair(kind: str, d: int) -> int:
-    """Matern32 direct form 3d+7, RBF 3d+4 (t = 1 right-hand side; sqrt, exp = 1 FLOP each)."""
+    """SURVEY.md 8d: Matern32 direct form 3d+7, RBF 3d+4 (t = 1 right-hand side; sqrt, exp = 1 FLOP each);
+    expanded/DMMA form 2d+10 for the wide (d > 32) path."""
+    if d > 32:
+        return 2 * d + 10 if kind == "matern32" else 2 * d + 7
     return 3 * d + 7 if kind == "matern32" else 3 * d + 4
 
 
@@ -312,7 +316,12 @@ def run_b200(args, rank, world, local_rank):
                      "traffic": traffic,
                      "note": "algorithmic-FLOP fraction: (3d+7) n^2 FLOP per K*v (SURVEY.md 8d) / CUDA-event time per launch; "
                              "FP64 has no tcgen05 path, the denominator is the measured DMMA.8x8x4 rate "
-                             "(profiles/fp64_peaks_r01.json, 'of measured'); the sweep evaluates each unordered pair once",
+                             "(profiles/fp64_peaks_r01.json, 'of measured'); the symmetric sweep evaluates each unordered pair once, so `achieved` "
+                             "(nominal n^2 pairs of the reference's K*v) can exceed the peak; `achieved_evaluated` counts only the pairs "
+                             "actually evaluated (n^2/2 + the diagonal blocks)",
+                     "achieved_evaluated": (achieved * (0.5 + 0.5 * min(1.0, (1024.0 if d <= 32 else 128.0) / n))) if achieved else None,
+                     "frac_evaluated": (achieved * (0.5 + 0.5 * min(1.0, (1024.0 if d <= 32 else 128.0) / n)) / fp64_peak) if achieved else None,
+                     "fp64_pipe_utilisation_ncu": ncu.get("fp64_pipe_active_pct"),
                      "launches": n_kmv, "ms_per_launch": kmv_ms,
                      "share_of_step": float(kt[0]) / float(t_dev[0]) if float(t_dev[0]) else None},
         "roofline_other": {

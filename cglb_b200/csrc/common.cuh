@@ -58,6 +58,9 @@ struct Context {
     unsigned long long launches;   // number of kernels this context launched (bench.py gpu_launches)
 };
 
+// the first kScratchScalars doubles of Context::scratch hold the scalar accumulators of the sweeps
+// (d + 1 gradient sums, d <= 128); everything else starts after them
+constexpr int kScratchScalars = 256;
 int ensure_vpad(Context* ctx, long n_pad);
 int ensure_scratch(Context* ctx, long n_doubles);
 

@@ -10,7 +10,7 @@
 // (cuSOLVER dpotrf, cuBLAS dtrsm/dgemm).  FP64 has no tcgen05 form; mma.sync.m8n8k4.f64 (DMMA) measured
 // 37.1 TFLOP/s on this B200 vs 34.2 for plain DFMA (profiles/fp64_peaks_r01.json), so the contraction
 // runs on DMMA.
-#include "common.cuh"
+#include "kmv_impl.cuh"
 
 namespace cglb {
 
@@ -21,7 +21,20 @@ constexpr int GSTAGES = 3;
 constexpr int GTHREADS = 256;
 constexpr int NB = 128;              // block size of the blocked factorisations
 
-enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_SYRK = 2 };
+enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_SYRK = 2, EPI_KMAP = 3, EPI_KBWD = 4 };
+
+// extra operands of the kernel-map epilogues (wide-input K_nm build / backward): the GEMM computes
+// S = Zp Xp^T, the epilogue turns it into variance*kappa(|z|^2+|x|^2-2S) (EPI_KMAP) or into
+// GP = (T + wt zvec^T) * e' * variance * cfac written over T, with sum G*kappa, row sums and column sums (EPI_KBWD)
+struct KEpiArgs {
+    const double* nz; long nz_stride;     // |z_m|^2 at nz[m * nz_stride]
+    const double* nx; long nx_stride;
+    const double* exp_tab;
+    const double* wt; const double* zvec;  // may be null
+    double* rsum; double* csum; double* gk_sum;
+    double variance, vc;
+    int kind;
+};
 
 struct GemmArgs {
     const double* A; long lda;
@@ -31,6 +44,7 @@ struct GemmArgs {
     long k_chunk;         // K range handled per blockIdx.z
     double alpha, beta;
     int lower_only;       // skip tiles strictly above the block diagonal
+    KEpiArgs ke;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
@@ -158,6 +172,73 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
     }
     cp_async_wait<0>();
 
+    if (EPI == EPI_KMAP || EPI == EPI_KBWD) {
+        __shared__ double s_tab[64];
+        __syncthreads();
+        if (tid < 64) s_tab[tid] = p.ke.exp_tab[tid];
+        __syncthreads();
+        double gk = 0.0, racc[8], cacc[4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) racc[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cacc[j][0] = cacc[j][1] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long row = m0 + wm * 64 + i * 8 + g;
+            const bool rlive = row < p.m;
+            const double nzr = rlive ? p.ke.nz[row * p.ke.nz_stride] : 0.0;
+            const double wtr = (EPI == EPI_KBWD && rlive && p.ke.wt) ? p.ke.wt[row] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const long cc = n0 + wn * 32 + j * 8 + 2 * t + e;
+                    if (!rlive || cc >= p.n) continue;
+                    const double q = fma(-2.0, acc[i][j][e], nzr + p.ke.nx[cc * p.ke.nx_stride]);
+                    double kap, ew;
+                    if (p.ke.kind == CGLB_MATERN32) kappa_and_dweight<CGLB_MATERN32>(q, s_tab, kap, ew);
+                    else kappa_and_dweight<CGLB_RBF>(q, s_tab, kap, ew);
+                    double* dst = p.C + row * p.ldc + cc;
+                    if (EPI == EPI_KMAP) {
+                        *dst = p.ke.variance * kap;
+                    } else {
+                        double G = (p.beta != 0.0) ? *dst : 0.0;            // beta != 0: a dense T is present
+                        if (p.ke.zvec) G = fma(wtr, p.ke.zvec[cc], G);
+                        const double gp = G * ew * p.ke.vc;
+                        *dst = gp;
+                        gk = fma(G, kap, gk);
+                        racc[i] += gp;
+                        cacc[j][e] += gp;
+                    }
+                }
+            }
+        }
+        if (EPI == EPI_KBWD) {
+            // rows: reduce over the 4 lanes sharing g; columns: over the 8 lanes sharing t
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double s = racc[i];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                const long row = m0 + wm * 64 + i * 8 + g;
+                if (t == 0 && row < p.m) atomicAdd(p.ke.rsum + row, s);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double s = cacc[j][e];
+                    s += __shfl_xor_sync(0xffffffffu, s, 4);
+                    s += __shfl_xor_sync(0xffffffffu, s, 8);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    const long cc = n0 + wn * 32 + j * 8 + 2 * t + e;
+                    if (g == 0 && cc < p.n) atomicAdd(p.ke.csum + cc, s);
+                }
+            gk = warp_sum(gk);
+            if (lane == 0) atomicAdd(p.ke.gk_sum, gk);
+        }
+        return;
+    }
     // epilogue: lane holds (row g, cols 2t, 2t+1) of every 8x8 tile
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -204,7 +285,7 @@ static int launch_gemm(Context* ctx, const GemmArgs& p, int ksplit, cudaStream_t
 
 static int gemm_checked(Context* ctx, int transb, long m, long n, long k, double alpha, const double* a, long lda,
                         const double* b, long ldb, double beta, double* c, long ldc, cudaStream_t st) {
-    GemmArgs p{a, lda, b, ldb, c, ldc, m, n, k, (k + GK - 1) / GK * GK, alpha, beta, 0};
+    GemmArgs p{a, lda, b, ldb, c, ldc, m, n, k, (k + GK - 1) / GK * GK, alpha, beta, 0, {}};
     if (p.k_chunk == 0) p.k_chunk = GK;
     return transb ? launch_gemm<true, EPI_STORE>(ctx, p, 1, st) : launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
 }
@@ -348,11 +429,11 @@ struct DenseWs {
 static int get_dense_ws(Context* ctx, long m, DenseWs& ws) {
     long nblk = (m + NB - 1) / NB;
     ws.m_pad = nblk * NB;
-    long need = nblk * NB * NB + ws.m_pad * ws.m_pad + 64;
+    long need = nblk * NB * NB + ws.m_pad * ws.m_pad + kScratchScalars;
     int rc = ensure_scratch(ctx, need + 64);
     if (rc) return rc;
     // first 64 doubles of scratch are reserved for the sweeps' scalar accumulators
-    ws.dinv = ctx->scratch + 64;
+    ws.dinv = ctx->scratch + kScratchScalars;
     ws.lhat = ws.dinv + nblk * NB * NB;
     return CGLB_OK;
 }
@@ -364,10 +445,96 @@ static int build_lhat(Context* ctx, const double* l, long m, long ldl, const Den
         long rows = (m - k * NB) < NB ? (m - k * NB) : NB;
         // A-operand: dinv_k (NB x NB, lda NB) restricted to `rows` rows; B-operand: l[k*NB.., 0:k*NB) (K = rows)
         GemmArgs p{ws.dinv + k * NB * NB, NB, l + k * NB * ldl, ldl, ws.lhat + k * NB * ws.m_pad, ws.m_pad,
-                   rows, k * NB, rows, NB, -1.0, 0.0, 0};
+                   rows, k * NB, rows, NB, -1.0, 0.0, 0, {}};
         int rc = launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
         if (rc) return rc;
     }
+    return CGLB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// wide-input (d > 32) K_nm build and backward through the DMMA GEMM + kernel-map epilogues
+// ---------------------------------------------------------------------------------------------
+__global__ void knm_wide_assemble_kernel(const double* __restrict__ zp, long m, const double* __restrict__ xp, long ncols, int d, int w, int kp,
+                                         const double* __restrict__ rsum, const double* __restrict__ csum, const double* __restrict__ gx,
+                                         const double* __restrict__ gk_sum, const double* __restrict__ ls, double cscale,
+                                         double* __restrict__ out_ls, double* __restrict__ out_var, double* __restrict__ out_z) {
+    // one block per input dimension q
+    const int q = blockIdx.x;
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (long mm = threadIdx.x; mm < m; mm += blockDim.x) {
+        const double z = zp[mm * w + q], r = rsum[mm], gxv = gx[mm * kp + q];
+        s += z * z * r - 2.0 * z * gxv;
+        if (out_z) atomicAdd(out_z + mm * d + q, -(cscale / ls[q]) * (z * r - gxv));
+    }
+    for (long i = threadIdx.x; i < ncols; i += blockDim.x) {
+        const double x = xp[i * w + q];
+        s = fma(x * x, csum[i], s);
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(out_ls + q, sh[0] / ls[q]);
+        if (q == 0) atomicAdd(out_var, *gk_sum);
+    }
+}
+
+int knm_build_wide(Context* ctx, int kind, const double* zp, long m, const double* xp, long n, int d, double variance,
+                   double* out, long ld, cudaStream_t st) {
+    const int kp = wide_kp(d), w = packed_width(d);
+    KEpiArgs ke{};
+    ke.nz = zp + kp; ke.nz_stride = w; ke.nx = xp + kp; ke.nx_stride = w; ke.exp_tab = ctx->exp_table;
+    ke.variance = variance; ke.kind = kind;
+    GemmArgs p{zp, w, xp, w, out, ld, m, n, kp, (kp + GK - 1) / GK * GK, 1.0, 0.0, 0, ke};
+    return launch_gemm<true, EPI_KMAP>(ctx, p, 1, st);
+}
+
+int knm_backward_wide(Context* ctx, int kind, const double* zp, long m, const double* xp, long ncols, int d, double variance,
+                      const double* lengthscale, double* t, long ldt, const double* wt, const double* zvec, double* out_ls,
+                      double* out_var, double* out_z, cudaStream_t st) {
+    if (!t) {
+        set_error("knm_backward: for d > %d the dense operand t is required (it is used as workspace and overwritten)", CGLB_MAX_REGISTER_D);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    const int kp = wide_kp(d), w = packed_width(d);
+    // workspace: [rsum m | csum ncols | gk 1 | gx m*kp]
+    const long need = m + ncols + 1 + m * kp;
+    int rc = ensure_scratch(ctx, kScratchScalars + need);
+    if (rc) return rc;
+    double* rsum = ctx->scratch + kScratchScalars;
+    double* csum = rsum + m;
+    double* gk = csum + ncols;
+    double* gx = gk + 1;
+    CGLB_CUDA_OK(cudaMemsetAsync(rsum, 0, sizeof(double) * need, st));
+    KEpiArgs ke{};
+    ke.nz = zp + kp; ke.nz_stride = w; ke.nx = xp + kp; ke.nx_stride = w; ke.exp_tab = ctx->exp_table;
+    ke.wt = wt; ke.zvec = zvec; ke.rsum = rsum; ke.csum = csum; ke.gk_sum = gk;
+    ke.variance = variance; ke.vc = variance * ((kind == CGLB_MATERN32) ? 1.0 : 2.0); ke.kind = kind;
+    // S = Zp Xp^T, epilogue writes GP over t (beta = 1 flags "t holds a dense G part")
+    GemmArgs p{zp, w, xp, w, t, ldt, m, ncols, kp, (kp + GK - 1) / GK * GK, 1.0, 1.0, 0, ke};
+    rc = launch_gemm<true, EPI_KBWD>(ctx, p, 1, st);
+    if (rc) return rc;
+    // GX = GP * Xp (coordinates): split-K over the columns
+    long tiles = (m + GM - 1) / GM;
+    long want = (2L * ctx->num_sms + tiles - 1) / tiles;
+    long max_split = (ncols + 255) / 256;
+    long ksplit = want < max_split ? want : max_split;
+    if (ksplit < 1) ksplit = 1;
+    long chunk = ((ncols + ksplit - 1) / ksplit + GK - 1) / GK * GK;
+    ksplit = (ncols + chunk - 1) / chunk;
+    GemmArgs pg{t, ldt, xp, w, gx, kp, m, kp, ncols, chunk, 1.0, 0.0, 0, {}};
+    rc = launch_gemm<false, EPI_ATOMIC>(ctx, pg, (int)ksplit, st);
+    if (rc) return rc;
+    const double cscale = (kind == CGLB_MATERN32) ? 1.7320508075688772935 : 0.70710678118654752440;
+    knm_wide_assemble_kernel<<<d, 256, 0, st>>>(zp, m, xp, ncols, d, w, kp, rsum, csum, gx, gk, lengthscale, cscale, out_ls, out_var, out_z);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
     return CGLB_OK;
 }
 
@@ -405,7 +572,7 @@ extern "C" int cglb_syrk(cglb_context* c, const double* a, long m, long n, long 
     if (ksplit > 65535) ksplit = 65535;
     long chunk = ((n + ksplit - 1) / ksplit + GK - 1) / GK * GK;
     ksplit = (n + chunk - 1) / chunk;
-    GemmArgs p{a, lda, a, lda, cm, ldc, m, m, n, chunk, 1.0, 0.0, 1};
+    GemmArgs p{a, lda, a, lda, cm, ldc, m, m, n, chunk, 1.0, 0.0, 1, {}};
     return launch_gemm<true, EPI_SYRK>(ctx, p, (int)ksplit, st);
 }
 
@@ -427,12 +594,12 @@ extern "C" int cglb_potrf(cglb_context* c, double* a, long m, long lda, int* inf
         long rows = m - r1;
         // panel: a[r1:, kNB:r1) <- a[r1:, kNB:r1) * dinv_k^T      (NT, in place: a CTA owns its rows)
         GemmArgs pp{a + r1 * lda + k * NB, lda, ws.dinv + k * NB * NB, NB, a + r1 * lda + k * NB, lda,
-                    rows, NB, NB, NB, 1.0, 0.0, 0};
+                    rows, NB, NB, NB, 1.0, 0.0, 0, {}};
         rc = launch_gemm<true, EPI_STORE>(ctx, pp, 1, st);
         if (rc) return rc;
         // trailing: a[r1:, r1:) -= P P^T  (lower tiles only)
         GemmArgs pt{a + r1 * lda + k * NB, lda, a + r1 * lda + k * NB, lda, a + r1 * lda + r1, lda,
-                    rows, rows, NB, NB, -1.0, 1.0, 1};
+                    rows, rows, NB, NB, -1.0, 1.0, 1, {}};
         rc = launch_gemm<true, EPI_STORE>(ctx, pt, 1, st);
         if (rc) return rc;
     }
@@ -465,7 +632,7 @@ extern "C" int cglb_tri_inverse(cglb_context* c, const double* l, long m, long l
     for (long k = 1; k < nblk; ++k) {
         long rows = (m - k * NB) < NB ? (m - k * NB) : NB;
         GemmArgs p{ws.lhat + k * NB * ws.m_pad, ws.m_pad, linv, ldi, linv + k * NB * ldi, ldi,
-                   rows, k * NB, k * NB, k * NB, 1.0, 0.0, 0};
+                   rows, k * NB, k * NB, k * NB, 1.0, 0.0, 0, {}};
         rc = launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
         if (rc) return rc;
     }
@@ -494,7 +661,7 @@ extern "C" int cglb_trsm_left_lower(cglb_context* c, const double* l, long m, lo
         long rows = (m - k * NB) < NB ? (m - k * NB) : NB;
         long kk = k * NB + rows;
         GemmArgs p{ws.lhat + k * NB * ws.m_pad, ws.m_pad, b, ldb, b + k * NB * ldb, ldb,
-                   rows, n, kk, (kk + GK - 1) / GK * GK, 1.0, 0.0, 0};
+                   rows, n, kk, (kk + GK - 1) / GK * GK, 1.0, 0.0, 0, {}};
         rc = launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
         if (rc) return rc;
     }

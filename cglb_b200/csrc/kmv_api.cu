@@ -104,11 +104,21 @@ sweep_fn get_sweep_fn(int d) {
     }
 }
 
+int knm_build_wide(Context* ctx, int kind, const double* zp, long m, const double* xp, long n, int d, double variance,
+                   double* out, long ld, cudaStream_t st);
+int knm_backward_wide(Context* ctx, int kind, const double* zp, long m, const double* xp, long ncols, int d, double variance,
+                      const double* lengthscale, double* t, long ldt, const double* wt, const double* zvec, double* out_ls,
+                      double* out_var, double* out_z, cudaStream_t st);
 int wide_sweep(Context* ctx, int kind, bool sym, const double* xp_rows, long nrows, const double* xp_cols, long ncols, int d,
                const double* vcol, double* y, double variance, int part, int nparts, cudaStream_t st);
 
+int wide_bwd_sweep(Context* ctx, int kind, const double* xp, long n, int d, const double* wcol, const double* ucol, double* rsum,
+                   double* gout, int part, int nparts, cudaStream_t st);
+
 static int dispatch(Context* ctx, int kind, int d, int mode, const SweepArgs& a, cudaStream_t st) {
-    if (d > CGLB_MAX_REGISTER_D && mode != 2)
+    if (d > CGLB_MAX_REGISTER_D && mode == 2)
+        return wide_bwd_sweep(ctx, kind, a.xp_rows, a.nrows, d, a.vcol, a.ucol, a.y, a.gout, a.part, a.nparts, st);
+    if (d > CGLB_MAX_REGISTER_D)
         return wide_sweep(ctx, kind, mode == 0, a.xp_rows, a.nrows, a.xp_cols, a.ncols, d, a.vcol, a.y, a.variance, a.part, a.nparts, st);
     sweep_fn f = get_sweep_fn(d);
     if (!f) {
@@ -199,12 +209,13 @@ extern "C" int cglb_kmv_bwd_sym(cglb_context* c, int kind, const double* xp, lon
     long v_pad = (n + 1023) / 1024 * 1024;
     int rc = ensure_vpad(ctx, v_pad);
     if (rc) return rc;
-    rc = ensure_scratch(ctx, 64);
+    CGLB_CHECK_ARG(d + 1 <= kScratchScalars, "d too large");
+    rc = ensure_scratch(ctx, kScratchScalars);
     if (rc) return rc;
     bwd_prologue_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(u, w, n, v_pad, ctx->upad, ctx->vpad, ctx->rsum);
     ctx->launches++;
     CGLB_LAUNCH_OK();
-    CGLB_CUDA_OK(cudaMemsetAsync(ctx->scratch, 0, sizeof(double) * 64, st));
+    CGLB_CUDA_OK(cudaMemsetAsync(ctx->scratch, 0, sizeof(double) * kScratchScalars, st));
     SweepArgs a{};
     a.xp_rows = xp; a.xp_cols = xp; a.vcol = ctx->vpad; a.ucol = ctx->upad; a.y = ctx->rsum; a.gout = ctx->scratch;
     a.nrows = n; a.ncols = n; a.exp_tab = ctx->exp_table; a.variance = variance; a.part = part; a.nparts = nparts;
@@ -224,6 +235,7 @@ extern "C" int cglb_knm_build(cglb_context* c, int kind, const double* zp, long 
     CGLB_CHECK_ARG(ctx && zp && xp && out, "null pointer");
     CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
     CGLB_CHECK_ARG(ld >= n, "ld >= n");
+    if (d > CGLB_MAX_REGISTER_D) return knm_build_wide(ctx, kind, zp, m, xp, n, d, variance, out, ld, (cudaStream_t)stream);
     knm_fn f = get_knm_fn(d);
     if (!f) {
         set_error("knm_build: d=%d has no instantiation in this build", d);
@@ -241,6 +253,9 @@ extern "C" int cglb_knm_backward(cglb_context* c, int kind, const double* zp, lo
     CGLB_CHECK_ARG(ctx && zp && xp && lengthscale && out_ls && out_var, "null pointer");
     CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
     CGLB_CHECK_ARG((wt == nullptr) == (zvec == nullptr), "wt and zvec go together");
+    if (d > CGLB_MAX_REGISTER_D)
+        return knm_backward_wide(ctx, kind, zp, m, xp, ncols, d, variance, lengthscale, const_cast<double*>(t), ldt, wt, zvec, out_ls,
+                                 out_var, out_z, (cudaStream_t)stream);
     knm_fn f = get_knm_fn(d);
     if (!f) {
         set_error("knm_backward: d=%d has no instantiation in this build", d);

@@ -247,11 +247,11 @@ using namespace cglb;
 extern "C" int cglb_dot(cglb_context* c, const double* x, const double* y, long n, double* out_dev, void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);
     CGLB_CHECK_ARG(ctx && x && y && out_dev, "null pointer");
-    int rc = ensure_scratch(ctx, 64 + kRedBlocks);
+    int rc = ensure_scratch(ctx, kScratchScalars + kRedBlocks);
     if (rc) return rc;
     // partials live in the first kRedBlocks doubles after the 64 reserved scalars... but the dense
     // workspaces reuse that region, so dot products must not be interleaved *inside* a dense call (they are not).
-    dot_kernel<<<red_blocks(n), kRedThreads, 0, (cudaStream_t)stream>>>(x, y, n, ctx->scratch + 64, ctx->counters + 0, out_dev);
+    dot_kernel<<<red_blocks(n), kRedThreads, 0, (cudaStream_t)stream>>>(x, y, n, ctx->scratch + kScratchScalars, ctx->counters + 0, out_dev);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;
@@ -261,9 +261,9 @@ extern "C" int cglb_quad_terms(cglb_context* c, long n, const double* err, const
                                double* out_dev, void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);
     CGLB_CHECK_ARG(ctx && err && Kv && v && r && out_dev, "null pointer");
-    int rc = ensure_scratch(ctx, 64 + kRedBlocks);
+    int rc = ensure_scratch(ctx, kScratchScalars + kRedBlocks);
     if (rc) return rc;
-    quad_terms_kernel<<<red_blocks(n), kRedThreads, 0, (cudaStream_t)stream>>>(err, Kv, v, r, n, ctx->scratch + 64,
+    quad_terms_kernel<<<red_blocks(n), kRedThreads, 0, (cudaStream_t)stream>>>(err, Kv, v, r, n, ctx->scratch + kScratchScalars,
                                                                               ctx->counters + 0, out_dev);
     ctx->launches++;
     CGLB_LAUNCH_OK();
@@ -320,9 +320,9 @@ extern "C" int cglb_precond_finish(cglb_context* c, const double* a, long m, lon
     CGLB_CHECK_ARG(ctx && a && lbinv && q && r && z && w_out && rz_dev, "null pointer");
     CGLB_CHECK_ARG(m * sizeof(double) <= 200 * 1024, "M too large for the shared-memory staged w");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = ensure_scratch(ctx, 64 + kRedBlocks + m);
+    int rc = ensure_scratch(ctx, kScratchScalars + kRedBlocks + m);
     if (rc) return rc;
-    double* t = ctx->scratch + 64 + kRedBlocks;
+    double* t = ctx->scratch + kScratchScalars + kRedBlocks;
     if (m > 0) {
         // t = LBinv q ; also clears w_out and *rz_dev
         trmv_lower_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(lbinv, m, q, t, w_out, m, rz_dev);

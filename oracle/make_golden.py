@@ -30,6 +30,7 @@ CASES = [
     ("house_like_warmstart", "matern32", 600, 11, 64, 0.01, 1.0, 1.66, 0.0, [1.0, 1.01, 0.99], 13),
     ("ragged_rbf_init", "rbf", 257, 2, 17, 1.0, 1.0, 1.0, 0.0, [1.0, 1.01], 14),
     ("wide_d_matern", "matern32", 300, 20, 32, 0.05, 1.0, 3.0, 0.0, [1.0], 15),
+    ("song_like_wide", "matern32", 350, 90, 40, 0.05, 1.0, 4.7, 0.0, [1.0, 1.01], 17),
     # restart branch of conjugate_gradient.py:70-75 exercised through LowerBoundCG(model, cg_opt=...)
     ("restart_path", "matern32", 400, 2, 6, 0.02, 1.5, 0.5, 0.0, [1.0], 16,
      dict(max_error=1e-3, restart_cg_iter=4, max_cg_iter=100)),

@@ -14,7 +14,7 @@ def pytest_configure(config):
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["snelson_like_init", "road_like_trained", "kin_like_rbf", "house_like_warmstart",
-                "ragged_rbf_init", "wide_d_matern", "restart_path"]
+                "ragged_rbf_init", "wide_d_matern", "song_like_wide", "restart_path"]
 GRAD_NAMES = ["raw_noise", "mean_constant", "inducing_points", "raw_outputscale", "raw_lengthscale"]
 
 

@@ -37,7 +37,10 @@ def _problem(n, d, seed, lsval=None):
 # ---- K1: matvec ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind,n,d", [("matern32", 1, 1), ("matern32", 2, 3), ("matern32", 300, 1), ("rbf", 777, 8),
                                       ("matern32", 2500, 11), ("rbf", 2049, 3), ("matern32", 1025, 5), ("rbf", 900, 16),
-                                      ("matern32", 640, 20), ("rbf", 513, 32), ("matern32", 1300, 13)])
+                                      ("matern32", 640, 20), ("rbf", 513, 32), ("matern32", 1300, 13),
+                                      # d > 32: DMMA distance contraction (song-shaped config)
+                                      ("matern32", 1, 40), ("matern32", 300, 33), ("rbf", 1500, 64), ("matern32", 2300, 90),
+                                      ("rbf", 129, 100)])
 def test_kmv_sym_matches_oracle(eng, kind, n, d):
     x, v, u, ls = _problem(n, d, seed=n + d)
     dev = eng.device
@@ -79,7 +82,7 @@ def test_kmv_duplicate_points_and_empty(eng):
 
 
 @pytest.mark.parametrize("kind,nr,nc,d", [("matern32", 100, 1000, 3), ("rbf", 1500, 333, 8), ("matern32", 64, 3000, 11),
-                                          ("matern32", 7, 129, 20)])
+                                          ("matern32", 7, 129, 20), ("matern32", 200, 1500, 90), ("rbf", 1100, 90, 48)])
 def test_kmv_rect_matches_oracle(eng, kind, nr, nc, d):
     g = torch.Generator().manual_seed(nr + nc)
     xr, xc = torch.randn(nr, d, generator=g, dtype=f64), torch.randn(nc, d, generator=g, dtype=f64)
@@ -95,7 +98,8 @@ def test_kmv_rect_matches_oracle(eng, kind, nr, nc, d):
 
 # ---- K2: backward sweep ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind,n,d", [("matern32", 300, 1), ("rbf", 777, 8), ("matern32", 2500, 11), ("rbf", 1030, 3),
-                                      ("matern32", 520, 20), ("rbf", 300, 32)])
+                                      ("matern32", 520, 20), ("rbf", 300, 32), ("matern32", 1100, 40), ("rbf", 1030, 64),
+                                      ("matern32", 1500, 90)])
 def test_backward_sweep_matches_autograd(eng, kind, n, d):
     x, v, u, ls = _problem(n, d, seed=3 * n + d)
     dev = eng.device
@@ -179,7 +183,7 @@ def test_bound_and_gradients_match_reference_golden(name):
 
 
 @pytest.mark.parametrize("kind,n,d,M,noise", [("matern32", 900, 3, 40, 0.05), ("rbf", 700, 8, 33, 0.3), ("matern32", 513, 11, 64, 0.01),
-                                              ("matern32", 400, 20, 24, 0.1)])
+                                              ("matern32", 400, 20, 24, 0.1), ("matern32", 1200, 90, 48, 0.05), ("rbf", 700, 40, 17, 0.2)])
 def test_bound_and_gradients_fixed_v_match_oracle(kind, n, d, M, noise):
     """With CG disabled (use_cache, as the reference's metrics path interface.py:621-625) every term is a
     deterministic function of v: compare at tight tolerance."""
@@ -245,8 +249,8 @@ def test_error_behaviour(eng):
         eng.potrf(bad)
     with pytest.raises(cb.CglbError):
         eng.pack("matern32", torch.zeros(4, 2, dtype=f64), torch.ones(2, dtype=f64, device=eng.device), None)
-    with pytest.raises(cb.CglbError):                                # d outside the register-resident range
-        eng.kmv_sym("rbf", eng.zeros(128, 92), 10, 90, eng.zeros(10), 1.0, 0.0)
+    with pytest.raises(cb.CglbError):                                # d beyond what the shared-memory tiles hold
+        eng.kmv_sym("rbf", eng.zeros(128, eng.packed_width(300)), 10, 300, eng.zeros(10), 1.0, 0.0)
 
 
 # ---- dense kernels ------------------------------------------------------------------------------------------------------------
