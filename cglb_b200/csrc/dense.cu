@@ -283,11 +283,40 @@ static int launch_gemm(Context* ctx, const GemmArgs& p, int ksplit, cudaStream_t
     return CGLB_OK;
 }
 
+__global__ void scale_matrix_kernel(double* c, long m, long n, long ldc, double beta) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * n) return;
+    double* p = c + (idx / n) * ldc + idx % n;
+    *p = (beta == 0.0) ? 0.0 : beta * *p;
+}
+
+// C = alpha A op(B) + beta C where C does not alias A or B: few output tiles and a long K are split over
+// blockIdx.z (C pre-scaled by beta, partial products accumulated with RED.ADD.F64) so that all SMs work.
+template <bool TRANSB>
+static int launch_gemm_auto(Context* ctx, GemmArgs p, cudaStream_t st) {
+    const long tiles = ((p.m + GM - 1) / GM) * ((p.n + GN - 1) / GN);
+    long ksplit = 1;
+    if (tiles > 0 && tiles * 2 <= ctx->num_sms && p.k >= 512) {
+        ksplit = ctx->num_sms / tiles;
+        const long max_split = p.k / 256;
+        if (ksplit > max_split) ksplit = max_split;
+    }
+    if (ksplit <= 1) return launch_gemm<TRANSB, EPI_STORE>(ctx, p, 1, st);
+    scale_matrix_kernel<<<(unsigned)((p.m * p.n + 255) / 256), 256, 0, st>>>(p.C, p.m, p.n, p.ldc, p.beta);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    p.k_chunk = ((p.k + ksplit - 1) / ksplit + GK - 1) / GK * GK;
+    ksplit = (p.k + p.k_chunk - 1) / p.k_chunk;
+    return launch_gemm<TRANSB, EPI_ATOMIC>(ctx, p, (int)ksplit, st);
+}
+
 static int gemm_checked(Context* ctx, int transb, long m, long n, long k, double alpha, const double* a, long lda,
                         const double* b, long ldb, double beta, double* c, long ldc, cudaStream_t st) {
     GemmArgs p{a, lda, b, ldb, c, ldc, m, n, k, (k + GK - 1) / GK * GK, alpha, beta, 0, {}};
     if (p.k_chunk == 0) p.k_chunk = GK;
-    return transb ? launch_gemm<true, EPI_STORE>(ctx, p, 1, st) : launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
+    const bool alias = (c == a) || (c == b);
+    if (alias) return transb ? launch_gemm<true, EPI_STORE>(ctx, p, 1, st) : launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
+    return transb ? launch_gemm_auto<true>(ctx, p, st) : launch_gemm_auto<false>(ctx, p, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -329,9 +358,17 @@ __global__ void __launch_bounds__(256, 1) diag_block_kernel(double* a, long lda,
             if (tid == 0) {
                 double d = s[j * DP1 + j];
                 if (!(d > 0.0)) { s_fail = 1; d = 1.0; }
-                d = sqrt(d);
-                sd[j] = d;
-                sr[j] = 1.0 / d;
+                // 1/sqrt(d): MUFU.RSQ64H seed + Newton steps (full fp64 accuracy), sqrt = d * rsqrt + one correction
+                double y;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+                double e = fma(-d * y, y, 1.0);
+                y = fma(y * fma(e, 0.375, 0.5), e, y);
+                e = fma(-d * y, y, 1.0);
+                y = fma(0.5 * y, e, y);
+                double sq = d * y;
+                sq = fma(fma(-sq, sq, d), 0.5 * y, sq);
+                sd[j] = sq;
+                sr[j] = y;
             }
             __syncthreads();
             const double rinv = sr[j];
@@ -446,7 +483,7 @@ static int build_lhat(Context* ctx, const double* l, long m, long ldl, const Den
         // A-operand: dinv_k (NB x NB, lda NB) restricted to `rows` rows; B-operand: l[k*NB.., 0:k*NB) (K = rows)
         GemmArgs p{ws.dinv + k * NB * NB, NB, l + k * NB * ldl, ldl, ws.lhat + k * NB * ws.m_pad, ws.m_pad,
                    rows, k * NB, rows, NB, -1.0, 0.0, 0, {}};
-        int rc = launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
+        int rc = launch_gemm<false, EPI_STORE>(ctx, p, 1, st);      // K = 128: nothing to split
         if (rc) return rc;
     }
     return CGLB_OK;
@@ -633,7 +670,7 @@ extern "C" int cglb_tri_inverse(cglb_context* c, const double* l, long m, long l
         long rows = (m - k * NB) < NB ? (m - k * NB) : NB;
         GemmArgs p{ws.lhat + k * NB * ws.m_pad, ws.m_pad, linv, ldi, linv + k * NB * ldi, ldi,
                    rows, k * NB, k * NB, k * NB, 1.0, 0.0, 0, {}};
-        rc = launch_gemm<false, EPI_STORE>(ctx, p, 1, st);
+        rc = launch_gemm_auto<false>(ctx, p, st);                   // skinny output, long K: split over the SMs
         if (rc) return rc;
     }
     return CGLB_OK;
