@@ -31,30 +31,30 @@ class _KmvFunction(torch.autograd.Function):
     def forward(ctx, lengthscale, variance, diag, v, op):
         eng = op.engine
         n, d = op.x1.shape
-        ls = lengthscale.detach().contiguous()
+        ls = lengthscale.detach().to(torch.float64).contiguous()
         xp = op.packed(ls)
-        vv = v.detach().reshape(-1).contiguous()
+        vv = v.detach().reshape(-1).to(torch.float64).contiguous()
         y = eng.kmv_sym(op.kind, xp, n, d, vv, float(variance), float(diag))
         ctx.op, ctx.xp = op, xp
         ctx.save_for_backward(ls, variance.detach(), diag.detach(), vv)
-        return y.reshape(v.shape)
+        return y.reshape(v.shape).to(v.dtype)
 
     @staticmethod
     def backward(ctx, gy):
         ls, variance, diag, vv = ctx.saved_tensors
         op, xp, eng = ctx.op, ctx.xp, ctx.op.engine
         n, d = op.x1.shape
-        u = gy.detach().reshape(-1).contiguous()
+        u = gy.detach().reshape(-1).to(torch.float64).contiguous()
         g_ls = g_var = g_diag = g_v = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             out = eng.zeros(d + 1)
             eng.kmv_bwd_sym(op.kind, xp, n, d, u, vv, float(variance), ls, out)
-            g_ls = out[:d].reshape(ls.shape)
-            g_var = out[d].reshape(variance.shape)
+            g_ls = out[:d].reshape(ls.shape).to(gy.dtype)
+            g_var = out[d].reshape(variance.shape).to(gy.dtype)
         if ctx.needs_input_grad[2]:
-            g_diag = (u * vv).sum().reshape(diag.shape)
+            g_diag = (u * vv).sum().reshape(diag.shape).to(gy.dtype)
         if ctx.needs_input_grad[3]:
-            g_v = eng.kmv_sym(op.kind, xp, n, d, u, float(variance), float(diag)).reshape(gy.shape)
+            g_v = eng.kmv_sym(op.kind, xp, n, d, u, float(variance), float(diag)).reshape(gy.shape).to(gy.dtype)
         return g_ls, g_var, g_diag, g_v, None
 
 
@@ -65,7 +65,12 @@ class KernelOperator:
                  detached: bool = False):
         if not (x1.is_cuda and x2.is_cuda):
             raise CglbError("kernel operators need CUDA inputs (cglb_b200 has no CPU fallback)")
-        self.kernel, self.x1, self.x2 = kernel, x1.detach().contiguous(), x2.detach().contiguous()
+        # the sm_100a kernels are fp64: fp32 models (set_default_float("fp32")) are promoted here and results
+        # are cast back to the caller's dtype
+        self.out_dtype = x1.dtype
+        self.kernel = kernel
+        self.x1 = x1.detach().to(torch.float64).contiguous()
+        self.x2 = self.x1 if (symmetric and x2 is x1) else x2.detach().to(torch.float64).contiguous()
         self.symmetric = symmetric
         self.diag_value = diag_value
         self.detached = detached
@@ -81,7 +86,7 @@ class KernelOperator:
     def add_diag(self, value) -> "KernelOperator":
         if not self.symmetric:
             raise CglbError("add_diag needs a square kernel operator")
-        value = torch.as_tensor(value, dtype=self.x1.dtype, device=self.x1.device).reshape(())
+        value = torch.as_tensor(value, dtype=self.out_dtype, device=self.x1.device).reshape(())
         total = value if self.diag_value is None else self.diag_value + value
         out = KernelOperator(self.kernel, self.x1, self.x2, True, total, self.detached)
         out._packed, out._shift = self._packed, self._shift
@@ -94,11 +99,12 @@ class KernelOperator:
         return out
 
     def packed(self, lengthscale: Tensor):
-        key = lengthscale.data_ptr(), lengthscale._version
-        if self._packed is None or self._packed[0] != key:
+        # re-pack only when the lengthscale VALUES changed (pointer identity is not reliable: the softplus
+        # transform returns a fresh tensor on every access)
+        if self._packed is None or not torch.equal(self._packed[0], lengthscale):
             xp1 = self.engine.pack(self.kind, self.x1, lengthscale, self._shift)
             xp2 = xp1 if self.symmetric else self.engine.pack(self.kind, self.x2, lengthscale, self._shift)
-            self._packed = (key, xp1, xp2, lengthscale)
+            self._packed = (lengthscale.clone(), xp1, xp2, lengthscale)
         return self._packed[1]
 
     def __matmul__(self, v: Tensor) -> Tensor:
@@ -111,22 +117,22 @@ class KernelOperator:
                 ls.requires_grad or var.requires_grad or diag.requires_grad or v.requires_grad)
             if needs_grad:
                 return _KmvFunction.apply(ls, var, diag, v, self)
-            lsd = ls.detach().contiguous()
+            lsd = ls.detach().to(torch.float64).contiguous()
             xp = self.packed(lsd)
             n, d = self.x1.shape
-            y = self.engine.kmv_sym(kind, xp, n, d, v.detach().reshape(-1).contiguous(), float(var), float(diag))
-            return y.reshape(v.shape)
-        lsd = ls.detach().contiguous()
+            y = self.engine.kmv_sym(kind, xp, n, d, v.detach().reshape(-1).to(torch.float64).contiguous(), float(var), float(diag))
+            return y.reshape(v.shape).to(v.dtype)
+        lsd = ls.detach().to(torch.float64).contiguous()
         self.packed(lsd)
         _, xp1, xp2, _ = self._packed
         n1, d = self.x1.shape
-        y = self.engine.kmv_rect(kind, xp1, n1, xp2, self.x2.shape[0], d, v.detach().reshape(-1).contiguous(), float(var))
-        return y.reshape(n1, *v.shape[1:])
+        y = self.engine.kmv_rect(kind, xp1, n1, xp2, self.x2.shape[0], d, v.detach().reshape(-1).to(torch.float64).contiguous(), float(var))
+        return y.reshape(n1, *v.shape[1:]).to(v.dtype)
 
     def evaluate(self) -> Tensor:
         """Dense matrix (delazify).  Only sensible for M-sized operators."""
         kind, ls, var = _kernel_pieces(self.kernel)
-        lsd = ls.detach().contiguous()
+        lsd = ls.detach().to(torch.float64).contiguous()
         self.packed(lsd)
         _, xp1, xp2, _ = self._packed
         n1, d = self.x1.shape
@@ -136,8 +142,8 @@ class KernelOperator:
         self.engine.knm_build(kind, xp1, n1, xp2, n2, d, float(var), out, ld)
         dense = out[:, :n2]
         if self.diag_value is not None:
-            dense = dense + self.diag_value.detach() * torch.eye(n1, dtype=dense.dtype, device=dense.device)
-        return dense
+            dense = dense + self.diag_value.detach().to(dense.dtype) * torch.eye(n1, dtype=dense.dtype, device=dense.device)
+        return dense.to(self.out_dtype)
 
 
 def delazify(obj):

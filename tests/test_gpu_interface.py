@@ -1,0 +1,90 @@
+"""GPU (-m gpu): the backend interface end to end -- create_model (ConditionalVariance init), the 4-phase
+SciPy optimisation loop (interface.py:445-543), metrics, save/load -- on a small synthetic problem."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cglb_b200 as cb
+from cglb_b200 import interface
+from cglb_b200.callbacks import Logger
+from oracle import cglb_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def fp64_default():
+    old = torch.get_default_dtype()
+    interface.set_default_float("fp64")
+    cb.B200.set_default_jitter("fp64")
+    yield
+    torch.set_default_dtype(old)
+
+
+def _data(n=600, d=2, seed=3):
+    x, y, _ = o.synthetic_problem(n + 100, d, 4, seed=seed)
+    x, y = x.numpy(), y.numpy().reshape(-1, 1)
+    return (x[:n], y[:n]), (x[n:], y[n:])
+
+
+def test_create_optimize_metrics_save_load(fp64_default, tmp_path):
+    train, test = _data()
+    backend = cb.BACKENDS["b200"]
+    backend.configure_backend(logdir=str(tmp_path), keops=True)
+    assert backend.get_default_float_str() == "fp64" and backend.get_default_float() == np.float64
+    cfg = cb.CGLBConfig(kernel=cb.Matern32Config(), inducing_variable=cb.InducingVariableConfig(32))
+    model = backend.create_model(cfg, train)
+    assert isinstance(model, cb.CGLB) and model.covar_module.inducing_points.shape == (32, 2)
+    # initial hyper-parameters of the reference (config.py:76,105)
+    pars = backend.model_parameters(model)
+    assert abs(float(pars[".likelihood.variance"]) - 1.0) < 1e-9 and np.allclose(pars[".kernel.lengthscales"], 1.0)
+    # inducing points are a subset of the training inputs (greedy conditional variance)
+    z = pars[".inducing_variable.Z"]
+    assert all(np.any(np.all(np.isclose(train[0], zi), axis=1)) for zi in z)
+
+    metrics = backend.metrics_fn(model, (train, test))
+    logger = Logger(metrics, holdout_interval=5)
+    lb = cb.LowerBoundCG(model)
+    loss0 = float(-lb((model.train_inputs[0], model.train_targets)))
+    results = backend.optimize(model, (train, test), 12, logger, "scipy")
+    assert sum(r.nit for r in results) >= 1
+    loss1 = float(-lb((model.train_inputs[0], model.train_targets)))
+    assert loss1 < loss0 - 1.0                                  # the bound improved
+    assert len(logger.feval_logs["steps"]) >= 1                 # CG statistics were logged per f-eval
+    m = metrics()
+    assert {"cg/steps", "cg/error", "loss", "train/rmse", "test/rmse", "train/nlpd", "test/nlpd"} <= set(m)
+    assert m["test/rmse"] < 1.0 and np.isfinite(m["test/nlpd"])
+    with pytest.raises(AssertionError):
+        backend.optimize(model, (train, test), 1, logger, "adam_0.1")
+
+    backend.save(model, str(tmp_path))
+    saved = json.load(open(os.path.join(tmp_path, "model.json")))
+    assert set(saved) == {".likelihood.variance", ".mean_function.c", ".inducing_variable.Z", ".kernel.lengthscales", ".kernel.variance"}
+    model2 = backend.create_model(cfg, train)
+    backend.load(model2, os.path.join(tmp_path, "model.json"))
+    p1, p2 = backend.model_parameters(model), backend.model_parameters(model2)
+    for k in p1:
+        assert np.allclose(p1[k], p2[k], rtol=1e-10, atol=1e-12), k
+
+
+def test_fp32_models_are_promoted(fp64_default):
+    """fp32 switch (interface.py:94-104): parameters and data may be fp32; the sm_100a kernels compute in fp64."""
+    interface.set_default_float("fp32")
+    try:
+        train, _ = _data(n=300)
+        cfg = cb.CGLBConfig(kernel=cb.SquaredExponentialConfig(), inducing_variable=cb.InducingVariableConfig(16))
+        model = cb.B200.create_model(cfg, train)
+        assert model.train_inputs[0].dtype == torch.float32
+        loss = -cb.LowerBoundCG(model)((model.train_inputs[0], model.train_targets))
+        grads = torch.autograd.grad(loss, list(model.parameters()))
+        assert loss.dtype == torch.float32 and all(g.dtype == torch.float32 and torch.isfinite(g).all() for g in grads)
+        x64, y64 = torch.as_tensor(train[0], dtype=torch.float64), torch.as_tensor(train[1], dtype=torch.float64).reshape(-1)
+        z = model.covar_module.inducing_points.detach().double().cpu()
+        p = o.OracleParams.from_values(1.0, 0.0, z, 1.0, 1.0)
+        ref = o.lower_bound("rbf", p, x64.float().double(), y64.float().double(), torch.zeros(300, 1, dtype=torch.float64))
+        assert abs(float(loss) + float(ref.bound)) <= 1e-4 * abs(float(ref.bound))
+    finally:
+        interface.set_default_float("fp64")
