@@ -328,7 +328,7 @@ constexpr int DP1 = NB + 1;
 
 // mode 0: factor the block (a <- L, upper zeroed) and write inv(L) to dinv; mode 1: block already
 // holds L (lower), only invert.  nb_actual = rows in this block (<= NB).  info: 1+block on failure.
-__global__ void __launch_bounds__(256, 1) diag_block_kernel(double* a, long lda, long m, long first_block,
+__global__ void __launch_bounds__(1024, 1) diag_block_kernel(double* a, long lda, long m, long first_block,
                                                             double* dinv_base, int mode, int* info) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s = reinterpret_cast<double*>(smem_raw);      // [NB][DP1]
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256, 1) diag_block_kernel(double* a, long lda,
     double* ablk = a + r0 * lda + r0;
     double* dinv = dinv_base + blk * (long)NB * NB;
     const int tid = threadIdx.x;
-    const int ty = tid >> 4, tx = tid & 15;
+    const int ty = tid >> 5, tx = tid & 31;      // 32 x 32 thread grid: the loops are latency-bound, TLP hides it
     if (tid == 0) s_fail = 0;
     // load lower triangle (incl. diag); pad with identity
     for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
@@ -374,10 +374,10 @@ __global__ void __launch_bounds__(256, 1) diag_block_kernel(double* a, long lda,
             const double rinv = sr[j];
             for (int i = j + 1 + tid; i < NB; i += blockDim.x) s[i * DP1 + j] *= rinv;
             __syncthreads();
-            // trailing update: s[i][k] -= s[i][j] * s[k][j] for j < k <= i   (16 x 16 thread grid)
-            for (int i = j + 1 + ty; i < NB; i += 16) {
+            // trailing update: s[i][k] -= s[i][j] * s[k][j] for j < k <= i   (32 x 32 thread grid)
+            for (int i = j + 1 + ty; i < NB; i += 32) {
                 const double lij = s[i * DP1 + j];
-                for (int k = j + 1 + tx; k <= i; k += 16) s[i * DP1 + k] = fma(-lij, s[k * DP1 + j], s[i * DP1 + k]);
+                for (int k = j + 1 + tx; k <= i; k += 32) s[i * DP1 + k] = fma(-lij, s[k * DP1 + j], s[i * DP1 + k]);
             }
             __syncthreads();
         }
@@ -409,9 +409,9 @@ __global__ void __launch_bounds__(256, 1) diag_block_kernel(double* a, long lda,
         for (int c = tid; c <= j; c += blockDim.x) s[c * DP1 + j] *= rinv;
         __syncthreads();
         // B[i][c] -= L[i][j] * X[j][c] for i > j, c <= j
-        for (int c = ty; c <= j; c += 16) {
+        for (int c = ty; c <= j; c += 32) {
             const double xjc = s[c * DP1 + j];
-            for (int i = j + 1 + tx; i < NB; i += 16) s[c * DP1 + i] = fma(-s[i * DP1 + j], xjc, s[c * DP1 + i]);
+            for (int i = j + 1 + tx; i < NB; i += 32) s[c * DP1 + i] = fma(-s[i * DP1 + j], xjc, s[c * DP1 + i]);
         }
         __syncthreads();
     }
@@ -427,7 +427,7 @@ static int launch_diag(Context* ctx, double* a, long lda, long m, long first_blo
                        int* info, cudaStream_t st) {
     size_t smem = diag_smem_bytes();
     CGLB_CUDA_OK(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    diag_block_kernel<<<(unsigned)nblocks, 256, smem, st>>>(a, lda, m, first_block, dinv, mode, info);
+    diag_block_kernel<<<(unsigned)nblocks, 1024, smem, st>>>(a, lda, m, first_block, dinv, mode, info);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;
