@@ -35,8 +35,12 @@ class InducingVariableConfig(Config):
 
     def init(self, data: Data, kernel_fn: Callable):
         """Greedy conditional-variance selection (robustgp.ConditionalVariance(sample=False), config.py:62-65)."""
-        from .inducing import ConditionalVariance
-        iv, _ = ConditionalVariance(sample=False)(data[0], self.num_variables, kernel_fn)
+        from .inducing import ConditionalVariance, conditional_variance_gpu
+        gpu_kernel = getattr(kernel_fn, "gpu_kernel", None)
+        if gpu_kernel is not None:            # device-resident variant (interface.py passes the kernel module along)
+            iv, _ = conditional_variance_gpu(data[0], self.num_variables, gpu_kernel)
+        else:
+            iv, _ = ConditionalVariance(sample=False)(data[0], self.num_variables, kernel_fn)
         return iv
 
 

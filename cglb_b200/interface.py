@@ -156,6 +156,7 @@ def _likelihood_and_kernel_for_sgpr(model_cfg: SGPRConfig, data: Data):     # in
         x2 = x1 if x2 is None else _to_tensor(x2)
         return base_kernel(x1, x2).evaluate().detach().cpu().numpy()
 
+    init_kernel_fn.gpu_kernel = base_kernel      # lets InducingVariableConfig.init run the selection on the device
     inducing_variable = _to_tensor(params["inducing_variable"](init_kernel_fn))
     kernel = InducingPointKernel(base_kernel, inducing_variable, likelihood=likelihood)
     return likelihood, kernel

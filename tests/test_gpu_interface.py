@@ -88,3 +88,39 @@ def test_fp32_models_are_promoted(fp64_default):
         assert abs(float(loss) + float(ref.bound)) <= 1e-4 * abs(float(ref.bound))
     finally:
         interface.set_default_float("fp64")
+
+
+def test_readme_command_shim(tmp_path):
+    """README command of the reference (README.md:35) through the CLI shim, on a small synthetic dataset."""
+    from click.testing import CliRunner
+    from cglb_b200.cli import main
+    old = torch.get_default_dtype()
+    try:
+        res = CliRunner().invoke(main, ["--keops", "-b", "b200", "-t", "fp64", "-l", str(tmp_path), "-s", "1", "train", "-n", "6",
+                                        "-d", "synthetic:500x2", "cglb", "-k", "Matern32", "-i", "ConditionalVariance", "-M", "24"],
+                                 catch_exceptions=False)
+        assert res.exit_code == 0, res.output
+        for name in ("model.json", "results.json", "logs.json"):
+            assert os.path.isfile(os.path.join(tmp_path, name))
+        results = json.load(open(os.path.join(tmp_path, "results.json")))
+        assert {"loss", "test/rmse", "test/nlpd", "cg/steps"} <= set(results) and results["test/rmse"] < 1.0
+    finally:
+        torch.set_default_dtype(old)
+
+
+def test_gpu_conditional_variance_matches_host_version(fp64_default):
+    from cglb_b200.inducing import ConditionalVariance, conditional_variance_gpu
+    train, _ = _data(n=3000, d=3)
+    kernel = interface.create_kernel(cb.Matern32Config(), train).cuda()
+    kernel.base_kernel.lengthscale = torch.tensor([0.7, 1.0, 1.4], dtype=torch.float64)
+
+    def host_kernel(x1, x2, full_cov=False):
+        x1t = torch.as_tensor(x1, dtype=torch.float64).cuda()
+        if not full_cov:
+            return kernel(x1t, diag=True).detach().cpu().numpy()
+        x2t = x1t if x2 is None else torch.as_tensor(x2, dtype=torch.float64).cuda()
+        return kernel(x1t, x2t).evaluate().detach().cpu().numpy()
+
+    z_cpu, idx_cpu = ConditionalVariance(sample=False)(train[0], 48, host_kernel)
+    z_gpu, idx_gpu = conditional_variance_gpu(train[0], 48, kernel)
+    assert np.array_equal(idx_cpu, idx_gpu) and np.array_equal(z_cpu, z_gpu)
