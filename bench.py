@@ -135,7 +135,7 @@ def run_reference(args, rank):
     sweeps = counts.get(key, {}).get("reference_sweeps_per_step", 8.0)
     # bounded sample: `rows` rows of the row-blocked K v (what the reference's CPU backend does for every
     # matvec) and `cols` columns of the M x n Nystrom algebra, timed and extrapolated to the full step.
-    rows = max(8, min(n, int(2.0e8 // max(n, 1))))            # ~2e8 kernel pairs per timed step
+    rows = max(8, min(n, int(2.0e8 // max(n, 1)), int(6.0e9 // (8.0 * n * d))))   # ~2e8 kernel pairs per timed step, <= 6 GB of differences
     cols = max(64, min(n, int(2.0e7 // M)))
 
     def step():
@@ -252,14 +252,23 @@ def run_b200(args, rank, world, local_rank):
             stats.append(dict(ms=t_dev, ms_e2e=t_e2e, cg=int(out.cg_stats.steps), matvecs=out.matvecs, loss=float(loss)))
         return t_dev, t_e2e
 
+    def note(msg):
+        if rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+    note(f"{desc}, theta={args.theta}, {world} GPU(s): {args.warmup} warm-up + {args.steps} timed steps")
     for i in range(args.warmup):
-        one_step(i, False)
+        td, _ = one_step(i, False)
+        note(f"warm-up step {i + 1}/{args.warmup}: {td / 1e3:.2f} s")
     eng.enable_timing(True)
     launches0 = eng.launch_count
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    times = [one_step(args.warmup + i, True) for i in range(args.steps)]
+    times = []
+    for i in range(args.steps):
+        times.append(one_step(args.warmup + i, True))
+        note(f"timed step {i + 1}/{args.steps}: {times[-1][0] / 1e3:.2f} s, CG iterations {stats[-1]['cg']}")
     clocks = sampler.stop() if sampler else None
     launches = eng.launch_count - launches0
     ksum = eng.timing_summary()
@@ -338,7 +347,8 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"bench_{args.workload}_{args.theta}_n{world}.json"), "w") as f:
+        tag = f"_n{n}" if args.n else ""
+        with open(os.path.join(ROOT, "gpurun_out", f"bench_{args.workload}{tag}_{args.theta}_n{world}.json"), "w") as f:
             json.dump(line, f, indent=1)
     except Exception:
         pass
@@ -354,7 +364,7 @@ def cpu_baseline(kind, n, d, M, th, stats):
     ls = torch.full((1, d), th["ls"](d), dtype=torch.float64)
     var = torch.tensor(th["variance"], dtype=torch.float64)
     v = torch.randn(n, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
-    rows = max(8, min(n, int(2.0e8 // n)))
+    rows = max(8, min(n, int(2.0e8 // n), int(6.0e9 // (8.0 * n * d))))      # ~2e8 pairs, <= 6 GB for the [rows, n, d] differences
     o.blocked_matvec_rows(kind, x, v, ls, var, 0, min(rows, 8))            # warm-up
     t0 = time.perf_counter()
     reps = 0

@@ -239,11 +239,44 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
         }
         return;
     }
-    // epilogue: lane holds (row g, cols 2t, 2t+1) of every 8x8 tile
+    // epilogue: lane holds (row g, cols 2t, 2t+1) of every 8x8 tile.  Per row group the (optional) reads of C
+    // are issued together before the dependent stores, as 16-byte accesses when C allows it.
+    const bool c_vec = ((p.ldc & 1) == 0) && (((uintptr_t)p.C & 15) == 0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const long row = m0 + wm * 64 + i * 8 + g;
         if (row >= p.m) continue;
+        if (EPI == EPI_STORE) {
+            double* crow = p.C + row * p.ldc;
+            double2 old[4];
+            bool full[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long col = n0 + wn * 32 + j * 8 + 2 * t;
+                full[j] = c_vec && (col + 1 < p.n);
+                old[j] = make_double2(0.0, 0.0);
+                if (p.beta != 0.0) {
+                    if (full[j]) old[j] = *reinterpret_cast<const double2*>(crow + col);
+                    else {
+                        if (col < p.n) old[j].x = crow[col];
+                        if (col + 1 < p.n) old[j].y = crow[col + 1];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long col = n0 + wn * 32 + j * 8 + 2 * t;
+                double2 v;
+                v.x = fma(p.beta, old[j].x, p.alpha * acc[i][j][0]);
+                v.y = fma(p.beta, old[j].y, p.alpha * acc[i][j][1]);
+                if (full[j]) *reinterpret_cast<double2*>(crow + col) = v;
+                else {
+                    if (col < p.n) crow[col] = v.x;
+                    if (col + 1 < p.n) crow[col + 1] = v.y;
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const long col = n0 + wn * 32 + j * 8 + 2 * t;
@@ -252,10 +285,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
                 const long cc = col + e;
                 if (cc >= p.n) continue;
                 const double val = p.alpha * acc[i][j][e];
-                if (EPI == EPI_STORE) {
-                    double* dst = p.C + row * p.ldc + cc;
-                    *dst = (p.beta == 0.0) ? val : fma(p.beta, *dst, val);
-                } else if (EPI == EPI_ATOMIC) {
+                if (EPI == EPI_ATOMIC) {
                     atomicAdd(p.C + row * p.ldc + cc, val);
                 } else {
                     atomicAdd(p.C + row * p.ldc + cc, val);

@@ -32,6 +32,24 @@ __global__ void __launch_bounds__(256) body(double* out, const double* tabg, int
                 for (int k = 0; k < D; ++k) q = fma(a2[ti][k], b[k], q);
                 double kk;
                 if (MODE == 0) kk = kappa<KIND>(q, s_tab);           // full map
+                else if (MODE == 7) {
+                    // trimmed Matern map: lower clamp only, 8n magic constant, LOP+LEA exponent add
+                    int hi = max(__double2hiint(q), 0x01700000);
+                    q = __hiloint2double(hi, __double2loint(q));
+                    double s = fast_sqrt(q);
+                    const double MAGIC8 = 54043195528445952.0, C8 = 8.0 * 92.332482616893656820, L8 = 1.0830424696249145255e-02 / 8.0;
+                    double t = fma(s, -C8, MAGIC8);
+                    int n8 = __double2loint(t);
+                    double nf8 = t - MAGIC8;
+                    double r = fma(nf8, -L8, -s);
+                    double p = fma(r, 8.3333333333333332177e-03, 4.1666666666666664354e-02);
+                    p = fma(p, r, 1.6666666666666665741e-01); p = fma(p, r, 0.5); p = fma(p, r, 1.0);
+                    double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_tab) + (n8 & 0x1F8));
+                    double Tr = T * r;
+                    double e = fma(Tr, p, T);
+                    e = __hiloint2double(__double2hiint(e) + ((n8 & ~0x1FF) << 11), __double2loint(e));
+                    kk = fma(s, e, e);
+                }
                 else if (MODE == 1) kk = q;                            // distance only
                 else if (MODE == 2) { q = clamp_sq_t<0x42F00000>(q); kk = fast_sqrt(q); }   // distance + sqrt
                 else {
@@ -83,6 +101,8 @@ int main() {
     double tab[64], *dtab; for (int j = 0; j < 64; ++j) tab[j] = exp2(j / 64.0);
     cudaMalloc(&dtab, sizeof(tab)); cudaMemcpy(dtab, tab, sizeof(tab), cudaMemcpyHostToDevice);
     run<CGLB_MATERN32, 11, 4, 0>("matern32 d=11 full", out, dtab, sms, 28);
+    run<CGLB_MATERN32, 11, 4, 7>("matern32 d=11 trimmed", out, dtab, sms, 28);
+    run<CGLB_MATERN32, 3, 4, 7>("matern32 d=3 trimmed", out, dtab, sms, 20);
     run<CGLB_MATERN32, 11, 2, 0>("matern32 d=11 full", out, dtab, sms, 28);
     run<CGLB_MATERN32, 11, 4, 1>("d=11 distance only", out, dtab, sms, 13);
     run<CGLB_MATERN32, 11, 4, 2>("d=11 distance+sqrt", out, dtab, sms, 18);
