@@ -54,7 +54,7 @@ struct Context {
     long vpad_cap;
     double* scratch;      // generic scratch (partials of reductions)
     long scratch_cap;
-    double* exp_table;    // 64 doubles 2^(j/64), staged into shared memory by the sweep kernels
+    double* exp_table;    // [64] 2^(j/64) followed by [1024] 2^(j/1024); staged into shared memory by the kernels
     unsigned long long launches;   // number of kernels this context launched (bench.py gpu_launches)
 };
 
@@ -146,24 +146,36 @@ __device__ __forceinline__ double fast_sqrt(double q) {
     return fma(g, t, g);
 }
 
-// exp(-s) for s >= 0 (s <= 2^30): n = rint(-s*64/ln2), r = -s - n ln2/64 (|r| <= ln2/128),
-// e^r by a degree-5 polynomial, 2^(n/64) from a 64-entry table in shared memory and an exponent-field
-// add.  9 FP64 slots + 1 LDS + integer work.  Results below 2^-1000 are not meaningful (treated as 0
-// by every consumer: they are multiplied into sums of O(1) terms).
+// exp(-s) for s >= 0: n = rint(-s*2^TB/ln2) by the magic-number add, r = -s - n ln2/2^TB, e^r by a short
+// polynomial, 2^(n/2^TB) from a 2^TB-entry table in shared memory and an exponent-field add.
+//   TB = 6  : 64-entry table, degree-5 polynomial, 9 FP64 slots  (small kernels: 512 B of shared memory)
+//   TB = 10 : 1024-entry table (8 KB), degree-3 polynomial with the r^4/24 term folded into the quadratic
+//             coefficient (Chebyshev), 7 FP64 slots, max rel. error 7e-17 + rounding      (the sweeps)
+// s must be <= 2^24 (TB = 6) resp. 2^20 (TB = 10) so that n fits an int32; results below 2^-1000 are
+// flushed to ~2^-1000 (every consumer multiplies them into sums of O(1) terms).
+constexpr int kExpTabSmall = 64;
+constexpr int kExpTabBig = 1024;
+template <int TB>
 __device__ __forceinline__ double fast_exp_neg(double s, const double* __restrict__ tab /* shared */) {
     const double MAGIC = 6755399441055744.0;              // 1.5 * 2^52
-    const double C = 92.332482616893656820;                // 64 / ln 2
-    const double L = 1.0830424696249145255e-02;            // ln 2 / 64
+    constexpr double C = (TB == 6) ? 92.332482616893656820 : 1477.3197218702985091;     // 2^TB / ln 2
+    constexpr double L = (TB == 6) ? 1.0830424696249145255e-02 : 6.7690154351557157843e-04;   // ln 2 / 2^TB
     double t = fma(s, -C, MAGIC);
     int n = __double2loint(t);
     double nf = t - MAGIC;
     double r = fma(nf, -L, -s);
-    double p = fma(r, 8.3333333333333332177e-03, 4.1666666666666664354e-02);
-    p = fma(p, r, 1.6666666666666665741e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    double T = tab[n & 63];
-    int m = max(n >> 6, -1000);
+    double p;
+    if (TB == 6) {
+        p = fma(r, 8.3333333333333332177e-03, 4.1666666666666664354e-02);
+        p = fma(p, r, 1.6666666666666665741e-01);
+        p = fma(p, r, 0.5);
+        p = fma(p, r, 1.0);
+    } else {
+        p = fma(r, 1.6666666666666665741e-01, 0.5 + 4.7730e-09);      // 1/2 + h^2/24, h = ln2/2048
+        p = fma(p, r, 1.0);
+    }
+    double T = tab[n & ((1 << TB) - 1)];
+    int m = max(n >> TB, -1000);
     double Tr = T * r;
     double res = fma(Tr, p, T);
     return __hiloint2double(__double2hiint(res) + (m << 20), __double2loint(res));

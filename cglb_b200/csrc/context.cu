@@ -80,8 +80,9 @@ extern "C" int cglb_create(cglb_context** out, int device) {
     ctx->num_sms = prop.multiProcessorCount;
     CGLB_CUDA_OK(cudaMalloc(&ctx->counters, sizeof(int) * 16));
     CGLB_CUDA_OK(cudaMemset(ctx->counters, 0, sizeof(int) * 16));
-    double tab[64];
-    for (int j = 0; j < 64; ++j) tab[j] = exp2((double)j / 64.0);
+    static double tab[kExpTabSmall + kExpTabBig];
+    for (int j = 0; j < kExpTabSmall; ++j) tab[j] = exp2((double)j / kExpTabSmall);
+    for (int j = 0; j < kExpTabBig; ++j) tab[kExpTabSmall + j] = exp2((double)j / kExpTabBig);
     CGLB_CUDA_OK(cudaMalloc(&ctx->exp_table, sizeof(tab)));
     CGLB_CUDA_OK(cudaMemcpy(ctx->exp_table, tab, sizeof(tab), cudaMemcpyHostToDevice));
     *out = reinterpret_cast<cglb_context*>(ctx);

@@ -51,30 +51,32 @@ __device__ __forceinline__ double clamp_sq_t(double q) {
 }
 
 // kappa(q): Matern32 -> (1+s) e^-s with s = sqrt(q) (inputs pre-scaled by sqrt3/l);  RBF -> e^-q
-template <int KIND>
+// TB selects the exp table (6: 64 entries / 9 slots, 10: 1024 entries / 7 slots); the clamp keeps
+// rint(-s * 2^TB / ln 2) inside int32: s <= 2^24 (TB 6) resp. 2^20 (TB 10).
+template <int KIND, int TB = 6>
 __device__ __forceinline__ double kappa(double q, const double* tab) {
     if (KIND == CGLB_MATERN32) {
-        q = clamp_sq_t<0x42F00000>(q);   // s <= 2^24 keeps rint(-s*64/ln2) inside int32
+        q = clamp_sq_t<(TB == 6) ? 0x42F00000 : 0x42700000>(q);
         double s = fast_sqrt(q);
-        double e = fast_exp_neg(s, tab);
+        double e = fast_exp_neg<TB>(s, tab);
         return fma(s, e, e);
     } else {
-        q = clamp_sq_t<0x41700000>(q);
-        return fast_exp_neg(q, tab);
+        q = clamp_sq_t<(TB == 6) ? 0x41700000 : 0x41300000>(q);
+        return fast_exp_neg<TB>(q, tab);
     }
 }
 
 // kappa and the lengthscale-derivative weight e' (Matern32: e^-s; RBF: e^-q, factor 2 applied by host)
-template <int KIND>
+template <int KIND, int TB = 6>
 __device__ __forceinline__ void kappa_and_dweight(double q, const double* tab, double& kap, double& ew) {
     if (KIND == CGLB_MATERN32) {
-        q = clamp_sq_t<0x42F00000>(q);
+        q = clamp_sq_t<(TB == 6) ? 0x42F00000 : 0x42700000>(q);
         double s = fast_sqrt(q);
-        ew = fast_exp_neg(s, tab);
+        ew = fast_exp_neg<TB>(s, tab);
         kap = fma(s, ew, ew);
     } else {
-        q = clamp_sq_t<0x41700000>(q);
-        ew = fast_exp_neg(q, tab);
+        q = clamp_sq_t<(TB == 6) ? 0x41700000 : 0x41300000>(q);
+        ew = fast_exp_neg<TB>(q, tab);
         kap = ew;
     }
 }
@@ -219,15 +221,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_sweep_kernel(const SweepArg
     ring.s_x = reinterpret_cast<double*>(smem_raw);                       // [kStages][kBJ*DP]
     ring.s_v = ring.s_x + kStages * kBJ * DP;                             // [kStages][kBJ]
     double* s_col = ring.s_v + kStages * kBJ;                             // [2][kWarps][kBJ]
-    double* s_tab = s_col + 2 * kWarps * kBJ;                             // [64]
-    ring.s_full = reinterpret_cast<uint64_t*>(s_tab + 64);                // [kStages]
+    double* s_tab = s_col + 2 * kWarps * kBJ;                             // [1024] 2^(j/1024)
+    ring.s_full = reinterpret_cast<uint64_t*>(s_tab + kExpTabBig);        // [kStages]
     ring.s_empty = ring.s_full + kStages;
     ring.pstage = ring.stage = 0;
     ring.pphase = ring.phase = 0;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    if (tid < 64) s_tab[tid] = args.exp_tab[tid];
+    for (int i = tid; i < kExpTabBig; i += kThreads) s_tab[i] = args.exp_tab[kExpTabSmall + i];
     if (tid == 0) ring.init_barriers();
     __syncthreads();
 
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_sweep_kernel(const SweepArg
 #pragma unroll
                     for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
-                        for (int ti = 0; ti < TI; ++ti) q[cb][ti] = kappa<KIND>(q[cb][ti], s_tab);
+                        for (int ti = 0; ti < TI; ++ti) q[cb][ti] = kappa<KIND, 10>(q[cb][ti], s_tab);
                     // phase 3: row / column accumulation
 #pragma unroll
                     for (int cb = 0; cb < CB; ++cb) {
@@ -354,8 +356,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_bwd_kernel(const SweepArgs 
     ring.s_x = reinterpret_cast<double*>(smem_raw);                       // [kStages][kBJ*DP]
     ring.s_v = ring.s_x + kStages * kBJ * DP;                             // [kStages][2][kBJ]  (w, u)
     double* s_col = ring.s_v + kStages * 2 * kBJ;                         // [2][kWarps][kBJ]
-    double* s_tab = s_col + 2 * kWarps * kBJ;                             // [64]
-    double* s_red = s_tab + 64;                                           // [kWarps][D+2]
+    double* s_tab = s_col + 2 * kWarps * kBJ;                             // [1024] 2^(j/1024)
+    double* s_red = s_tab + kExpTabBig;                                   // [kWarps][D+2]
     ring.s_full = reinterpret_cast<uint64_t*>(s_red + kWarps * (D + 2));
     ring.s_empty = ring.s_full + kStages;
     ring.pstage = ring.stage = 0;
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_bwd_kernel(const SweepArgs 
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    if (tid < 64) s_tab[tid] = args.exp_tab[tid];
+    for (int i = tid; i < kExpTabBig; i += kThreads) s_tab[i] = args.exp_tab[kExpTabSmall + i];
     if (tid == 0) ring.init_barriers();
     __syncthreads();
 
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_bwd_kernel(const SweepArgs 
 #pragma unroll
                         for (int k = 0; k < D; ++k) q = fma(a2[ti][k], b[k], q);
                         double kap, ew;
-                        kappa_and_dweight<KIND>(q, s_tab, kap, ew);
+                        kappa_and_dweight<KIND, 10>(q, s_tab, kap, ew);
                         const double om = fma(wi[ti], uj, ui[ti] * wj);
                         const double cw = ew * om;
                         gvar = fma(kap, om, gvar);
@@ -660,12 +662,12 @@ static int run_knm(Context* ctx, int bwd, const KnmArgs& a, cudaStream_t st) {
 template <int D, int WARPS>
 static size_t fwd_smem_bytes() {
     constexpr int DP = SmemLayout<D>::DP;
-    return (size_t)(kStages * kBJ * DP + kStages * kBJ + 2 * WARPS * kBJ + 64) * sizeof(double) + 2 * kStages * sizeof(uint64_t);
+    return (size_t)(kStages * kBJ * DP + kStages * kBJ + 2 * WARPS * kBJ + kExpTabBig) * sizeof(double) + 2 * kStages * sizeof(uint64_t);
 }
 template <int D, int WARPS>
 static size_t bwd_smem_bytes() {
     constexpr int DP = SmemLayout<D>::DP;
-    return (size_t)(kStages * kBJ * DP + kStages * 2 * kBJ + 2 * WARPS * kBJ + 64 + WARPS * (D + 2)) * sizeof(double) +
+    return (size_t)(kStages * kBJ * DP + kStages * 2 * kBJ + 2 * WARPS * kBJ + kExpTabBig + WARPS * (D + 2)) * sizeof(double) +
            2 * kStages * sizeof(uint64_t);
 }
 

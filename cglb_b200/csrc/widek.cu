@@ -56,15 +56,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_sweep_kernel(const WideArg
     double* s_v = s_cols + 2 * WT_COLS * W;                               // [2][64]
     double* s_col = s_v + 2 * WT_COLS;                                    // [2][4][64] per row-warp column sums, by tile parity
     double* s_row = s_col + 8 * WT_COLS;                                  // [2][128]  per col-warp row sums
-    double* s_tab = s_row + 2 * WT_ROWS;                                  // [64]
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_tab + 64);           // [2] column tiles
+    double* s_tab = s_row + 2 * WT_ROWS;                                  // [64] (DMMA-dominated: the small exp table keeps d <= 104 in 227 KB)
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_tab + kExpTabSmall); // [2] column tiles
     uint64_t* s_empty = s_full + 2;                                       // [2]
     uint64_t* s_rowbar = s_empty + 2;                                     // [1] row tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
-    if (tid < 64) s_tab[tid] = args.exp_tab[tid];
+    if (tid < kExpTabSmall) s_tab[tid] = args.exp_tab[tid];
     if (tid == 0) {
         mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
         mbar_init(&s_empty[0], 8); mbar_init(&s_empty[1], 8);
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_sweep_kernel(const WideArg
 }
 
 static size_t wide_smem_bytes(int w) {
-    return (size_t)(WT_ROWS * w + 2 * WT_COLS * w + 2 * WT_COLS + 8 * WT_COLS + 2 * WT_ROWS + 64) * sizeof(double) + 8 * sizeof(uint64_t);
+    return (size_t)(WT_ROWS * w + 2 * WT_COLS * w + 2 * WT_COLS + 8 * WT_COLS + 2 * WT_ROWS + kExpTabSmall) * sizeof(double) + 8 * sizeof(uint64_t);
 }
 
 int wide_sweep(Context* ctx, int kind, bool sym, const double* xp_rows, long nrows, const double* xp_cols, long ncols, int d,
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_bwd_kernel(const WideBwdAr
     double* s_row = s_col + 4 * WT_COLS;                                  // [4][64]     row sums per column warp
     double* s_xq = s_row + 4 * WB_ROWS;                                   // [8][NQ*8]
     double* s_tab = s_xq + 8 * NQ * 8;                                    // [64]
-    double* s_red = s_tab + 64;                                           // [8]
+    double* s_red = s_tab + kExpTabSmall;                                 // [8]
     uint64_t* s_full = reinterpret_cast<uint64_t*>(s_red + 8);
     uint64_t* s_empty = s_full + 2;
     uint64_t* s_rowbar = s_empty + 2;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_bwd_kernel(const WideBwdAr
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const int wm = warp >> 2, wn = warp & 3;
-    if (tid < 64) s_tab[tid] = args.exp_tab[tid];
+    if (tid < kExpTabSmall) s_tab[tid] = args.exp_tab[tid];
     if (tid == 0) {
         mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
         mbar_init(&s_empty[0], 8); mbar_init(&s_empty[1], 8);
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_bwd_kernel(const WideBwdAr
 
 template <int NQ>
 static size_t wide_bwd_smem_bytes(int w) {
-    return (size_t)(WB_ROWS * w + 2 * WT_COLS * w + WB_ROWS * WB_CP + 4 * WT_COLS + 4 * WT_COLS + 4 * WB_ROWS + 8 * NQ * 8 + 64 + 8) * sizeof(double) +
+    return (size_t)(WB_ROWS * w + 2 * WT_COLS * w + WB_ROWS * WB_CP + 4 * WT_COLS + 4 * WT_COLS + 4 * WB_ROWS + 8 * NQ * 8 + kExpTabSmall + 8) * sizeof(double) +
            8 * sizeof(uint64_t);
 }
 

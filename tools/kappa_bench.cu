@@ -8,8 +8,9 @@ sweep_fn get_sweep_fn(int) { return nullptr; } knm_fn get_knm_fn(int) { return n
 
 template <int KIND, int D, int TI, int MODE>
 __global__ void __launch_bounds__(256) body(double* out, const double* tabg, int iters, double seed) {
-    __shared__ double s_tab[64];
-    if (threadIdx.x < 64) s_tab[threadIdx.x] = tabg[threadIdx.x];
+    __shared__ double s_tab[1024];
+    if (MODE == 8) { for (int i = threadIdx.x; i < 1024; i += 256) s_tab[i] = exp2(i / 1024.0); }
+    else if (threadIdx.x < 64) s_tab[threadIdx.x] = tabg[threadIdx.x];
     __syncthreads();
     double a2[TI][D], na[TI], racc[TI];
 #pragma unroll
@@ -48,6 +49,25 @@ __global__ void __launch_bounds__(256) body(double* out, const double* tabg, int
                     double Tr = T * r;
                     double e = fma(Tr, p, T);
                     e = __hiloint2double(__double2hiint(e) + ((n8 & ~0x1FF) << 11), __double2loint(e));
+                    kk = fma(s, e, e);
+                }
+                else if (MODE == 8) {
+                    // 1024-entry table, degree-3 polynomial: exp in 7 FP64 slots
+                    int hi = max(__double2hiint(q), 0x01700000); hi = min(hi, 0x42700000);
+                    q = __hiloint2double(hi, __double2loint(q));
+                    double s = fast_sqrt(q);
+                    const double MAGIC = 6755399441055744.0, C = 1477.3197218702985, L = 6.7690154351557158e-04;
+                    double t = fma(s, -C, MAGIC);
+                    int n = __double2loint(t);
+                    double nf = t - MAGIC;
+                    double r = fma(nf, -L, -s);
+                    double p = fma(r, 1.6666666666666665741e-01, 0.5);
+                    p = fma(p, r, 1.0);
+                    double T = s_tab[n & 1023];
+                    int m = max(n >> 10, -1000);
+                    double Tr = T * r;
+                    double e = fma(Tr, p, T);
+                    e = __hiloint2double(__double2hiint(e) + (m << 20), __double2loint(e));
                     kk = fma(s, e, e);
                 }
                 else if (MODE == 1) kk = q;                            // distance only
@@ -102,6 +122,8 @@ int main() {
     cudaMalloc(&dtab, sizeof(tab)); cudaMemcpy(dtab, tab, sizeof(tab), cudaMemcpyHostToDevice);
     run<CGLB_MATERN32, 11, 4, 0>("matern32 d=11 full", out, dtab, sms, 28);
     run<CGLB_MATERN32, 11, 4, 7>("matern32 d=11 trimmed", out, dtab, sms, 28);
+    run<CGLB_MATERN32, 11, 4, 8>("matern32 d=11 tab1024 deg3", out, dtab, sms, 26);
+    run<CGLB_MATERN32, 3, 4, 8>("matern32 d=3 tab1024 deg3", out, dtab, sms, 18);
     run<CGLB_MATERN32, 3, 4, 7>("matern32 d=3 trimmed", out, dtab, sms, 20);
     run<CGLB_MATERN32, 11, 2, 0>("matern32 d=11 full", out, dtab, sms, 28);
     run<CGLB_MATERN32, 11, 4, 1>("d=11 distance only", out, dtab, sms, 13);
