@@ -25,7 +25,7 @@ NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nv
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr"]
-PLAIN_UNITS = ["context.cu", "kmv_api.cu", "dense.cu", "vecops.cu", "knm.cu", "widek.cu"]
+PLAIN_UNITS = ["context.cu", "kmv_api.cu", "dense.cu", "vecops.cu", "knm.cu", "widek.cu", "dsweep.cu"]
 ALL_DIMS = list(range(1, 33))
 
 
@@ -75,6 +75,8 @@ def build(verbose: bool = True) -> str:
         if not os.path.exists(src):
             continue
         defs = [f"-DCGLB_KMV_DIMS_LIST={dims_list}"] if u == "kmv_api.cu" else []
+        if u == "dsweep.cu":
+            defs = os.environ.get("CGLB_EXTRA_DEFS", "").split()
         jobs.append((src, os.path.join(OBJ, u.replace(".cu", ".o")), defs))
     extra = os.environ.get("CGLB_EXTRA_DEFS", "").split()      # e.g. -DCGLB_KMV_EXPERIMENT (developer builds)
     for d in dims:

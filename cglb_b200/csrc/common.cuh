@@ -146,13 +146,16 @@ __device__ __forceinline__ double fast_sqrt(double q) {
     return fma(g, t, g);
 }
 
-// exp(-s) for s >= 0: n = rint(-s*2^TB/ln2) by the magic-number add, r = -s - n ln2/2^TB, e^r by a short
+// exp(-s) for 0 <= s <= 693: n = rint(-s*2^TB/ln2) by the magic-number add, r = -s - n ln2/2^TB, e^r by a short
 // polynomial, 2^(n/2^TB) from a 2^TB-entry table in shared memory and an exponent-field add.
 //   TB = 6  : 64-entry table, degree-5 polynomial, 9 FP64 slots  (small kernels: 512 B of shared memory)
 //   TB = 10 : 1024-entry table (8 KB), degree-3 polynomial with the r^4/24 term folded into the quadratic
 //             coefficient (Chebyshev), 7 FP64 slots, max rel. error 7e-17 + rounding      (the sweeps)
-// s must be <= 2^24 (TB = 6) resp. 2^20 (TB = 10) so that n fits an int32; results below 2^-1000 are
-// flushed to ~2^-1000 (every consumer multiplies them into sums of O(1) terms).
+// The caller clamps s to [0, 693] (kappa() does it on the squared distance with two integer min/max), so
+// e^-s >= 2^-1000 and the exponent-field add cannot wrap: no separate exponent clamp.
+// Instruction diet (profiles/README_r02.md): every non-FP64 instruction costs the FP64 pipe ~1 issue cycle in
+// these kernels, and a DFMA reading three distinct vector registers issues at 2/3 rate (tools/fp64_issue_model.cu);
+// hence e^r = T * (1 + r p) as DFMA(2 regs + imm) + DMUL and the exponent insert as LOP3 + IMAD.
 constexpr int kExpTabSmall = 64;
 constexpr int kExpTabBig = 1024;
 template <int TB>
@@ -175,10 +178,10 @@ __device__ __forceinline__ double fast_exp_neg(double s, const double* __restric
         p = fma(p, r, 1.0);
     }
     double T = tab[n & ((1 << TB) - 1)];
-    int m = max(n >> TB, -1000);
-    double Tr = T * r;
-    double res = fma(Tr, p, T);
-    return __hiloint2double(__double2hiint(res) + (m << 20), __double2loint(res));
+    double res = T * fma(r, p, 1.0);
+    int hi;      // hi(res) + ((n >> TB) << 20)
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(n & ~((1 << TB) - 1)), "n"(1 << (20 - TB)), "r"(__double2hiint(res)));
+    return __hiloint2double(hi, __double2loint(res));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

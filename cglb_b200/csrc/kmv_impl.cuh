@@ -51,17 +51,21 @@ __device__ __forceinline__ double clamp_sq_t(double q) {
 }
 
 // kappa(q): Matern32 -> (1+s) e^-s with s = sqrt(q) (inputs pre-scaled by sqrt3/l);  RBF -> e^-q
-// TB selects the exp table (6: 64 entries / 9 slots, 10: 1024 entries / 7 slots); the clamp keeps
-// rint(-s * 2^TB / ln 2) inside int32: s <= 2^24 (TB 6) resp. 2^20 (TB 10).
+// TB selects the exp table (6: 64 entries / 9 slots, 10: 1024 entries / 7 slots).  The squared distance is clamped
+// to [2^-1000, 693^2] resp. [2^-1000, 693] with two integer min/max on its high word (no FP64 slot): the lower
+// bound absorbs the tiny negative values of the expanded form and the diagonal, the upper bound keeps
+// e^-s >= 2^-1000 (so fast_exp_neg needs no exponent clamp; kernel values below 1e-301 are flushed to ~1e-301).
+constexpr int kClampHiMatern = 0x411d4fe4;   // high word of 693^2
+constexpr int kClampHiRbf = 0x4085a800;      // high word of 693
 template <int KIND, int TB = 6>
 __device__ __forceinline__ double kappa(double q, const double* tab) {
     if (KIND == CGLB_MATERN32) {
-        q = clamp_sq_t<(TB == 6) ? 0x42F00000 : 0x42700000>(q);
+        q = clamp_sq_t<kClampHiMatern>(q);
         double s = fast_sqrt(q);
         double e = fast_exp_neg<TB>(s, tab);
         return fma(s, e, e);
     } else {
-        q = clamp_sq_t<(TB == 6) ? 0x41700000 : 0x41300000>(q);
+        q = clamp_sq_t<kClampHiRbf>(q);
         return fast_exp_neg<TB>(q, tab);
     }
 }
@@ -70,12 +74,12 @@ __device__ __forceinline__ double kappa(double q, const double* tab) {
 template <int KIND, int TB = 6>
 __device__ __forceinline__ void kappa_and_dweight(double q, const double* tab, double& kap, double& ew) {
     if (KIND == CGLB_MATERN32) {
-        q = clamp_sq_t<(TB == 6) ? 0x42F00000 : 0x42700000>(q);
+        q = clamp_sq_t<kClampHiMatern>(q);
         double s = fast_sqrt(q);
         ew = fast_exp_neg<TB>(s, tab);
         kap = fma(s, ew, ew);
     } else {
-        q = clamp_sq_t<(TB == 6) ? 0x41700000 : 0x41300000>(q);
+        q = clamp_sq_t<kClampHiRbf>(q);
         ew = fast_exp_neg<TB>(q, tab);
         kap = ew;
     }

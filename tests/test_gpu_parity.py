@@ -54,6 +54,59 @@ def test_kmv_sym_matches_oracle(eng, kind, n, d):
     assert float((parts.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
 
 
+# ---- K1 on DMMA (dsweep.cu): the path the n >= 24k, d in {10, 11, 18, 19, 26, 27} sweeps take -------------------------
+@pytest.mark.parametrize("kind,n,d,lsval", [("matern32", 1, 11, None), ("matern32", 257, 11, None), ("matern32", 2500, 11, None),
+                                            ("rbf", 1500, 10, 2.0), ("matern32", 3333, 19, 2.0), ("rbf", 1111, 27, 3.0),
+                                            ("rbf", 1300, 18, None), ("matern32", 900, 26, None), ("matern32", 1300, 2, 0.7),
+                                            ("rbf", 2049, 3, None), ("matern32", 1500, 11, 0.05), ("matern32", 1500, 10, 30.0)])
+def test_dmma_sweep_matches_oracle(eng, monkeypatch, kind, n, d, lsval):
+    """CGLB_DSWEEP=2 forces the DMMA-distance sweep on shapes the size rule would give to the register kernel."""
+    monkeypatch.setenv("CGLB_DSWEEP", "2")
+    x, v, u, ls = _problem(n, d, seed=n + d, lsval=lsval)
+    dev = eng.device
+    xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    K = o.kernel_dense(kind, x, x, ls, torch.tensor(1.3, dtype=f64))
+    ref = K @ v + 0.07 * v
+    y = eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.3, 0.07)
+    assert float((y.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
+    parts = sum(eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.3, 0.07, part=p, nparts=3) for p in range(3))
+    assert float((parts.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
+    monkeypatch.setenv("CGLB_DSWEEP", "0")
+    y0 = eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.3, 0.07)
+    # both are expanded-form kernels: at the tiny-lengthscale case their cancellation errors (|a|^2 ~ 1e5) differ
+    assert float((y - y0).norm() / y0.norm()) <= (1e-12 if lsval is None else 1e-11)
+
+
+def test_dmma_sweep_duplicates_and_midsize(eng, monkeypatch):
+    dev = eng.device
+    # exact duplicates: zero and slightly negative expanded-form distances
+    x = torch.randn(40, 11, dtype=f64, generator=torch.Generator().manual_seed(1)).repeat(8, 1)
+    n, d = x.shape
+    ls = torch.full((d,), 1.2, dtype=f64)
+    v = torch.randn(n, dtype=f64, generator=torch.Generator().manual_seed(2))
+    monkeypatch.setenv("CGLB_DSWEEP", "2")
+    for kind in ("matern32", "rbf"):
+        xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+        y = eng.kmv_sym(kind, xp, n, d, v.to(dev), 2.0, 0.5)
+        ref = o.kernel_dense(kind, x, x, ls, torch.tensor(2.0, dtype=f64)) @ v + 0.5 * v
+        assert float((y.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
+    # mid size, n not a multiple of anything: the size rule picks the DMMA sweep by itself; it must agree with the
+    # register-resident sweep and its 8-way partition must sum to the full product
+    n, d = 60001, 11
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(n, d, generator=g, dtype=f64, device=dev)
+    v = torch.randn(n, generator=g, dtype=f64, device=dev)
+    ls = torch.full((d,), 1.5, dtype=f64, device=dev)
+    xp = eng.pack("matern32", x, ls, x.mean(0))
+    monkeypatch.delenv("CGLB_DSWEEP")
+    y1 = eng.kmv_sym("matern32", xp, n, d, v, 1.0, 0.01)
+    parts = sum(eng.kmv_sym("matern32", xp, n, d, v, 1.0, 0.01, part=p, nparts=8) for p in range(8))
+    monkeypatch.setenv("CGLB_DSWEEP", "0")
+    y0 = eng.kmv_sym("matern32", xp, n, d, v, 1.0, 0.01)
+    assert float((y1 - y0).norm() / y0.norm()) <= 1e-12
+    assert float((parts - y0).norm() / y0.norm()) <= 1e-12
+
+
 @pytest.mark.parametrize("kind,d,lsval", [("matern32", 3, 0.05), ("rbf", 3, 0.05), ("matern32", 8, 30.0)])
 def test_kmv_extreme_lengthscales(eng, kind, d, lsval):
     """expanded-form distances must survive tiny lengthscales (huge |a|^2) and huge ones (K ~ all ones)."""
