@@ -1,0 +1,275 @@
+// K1 for d <= 32 with the distance contraction on DMMA.8x8x4 ("dsweep").
+//
+// Why: on sm_100a every non-FP64 instruction of these sweeps costs the shared FP64/DMMA pipe about one issue
+// cycle (measured: profiles/README_r02.md, tools/fp64_issue_model.cu, tools/fp64_mix_model.cu).  In the
+// register-resident sweep (kmv_impl.cuh) a Matern32 pair at d = 11 is 27 FP64 instructions + ~15 integer / LDS /
+// MUFU instructions.  DMMA.8x8x4 performs the 256 FMAs of 8 warp-wide DFMAs in ONE instruction (same pipe
+// time), so moving the d + 1 distance FMAs onto it removes ~11 instructions per pair and most of the LDS
+// traffic; the kernel map runs on the accumulator fragments as in widek.cu.  Measured on B200 (Gpairs/s, DMMA vs
+// register kernel): d = 11 961 vs 914, d = 15 841 vs 697, d = 19 766 vs 644, d = 23 708 vs 580, d = 27 655 vs
+// 520; no gain for d < 10 (the register kernel keeps those).
+//
+// Works directly on the packed layout of cglb_pack_inputs (row width DP = d + 1 rounded up to even).  The
+// contraction length is DP rounded up to a multiple of 4; when DP is not one (d = 12, 13, 16, 17, ...) the
+// last k-step reads two doubles of the NEXT packed row, which the A side multiplies by 0.  DP = 12, 20, 28
+// (d = 10, 11, 18, 19, 26, 27) are = 4 or 12 mod 16 and bank-conflict free; the other widths take 2- to 8-way
+// conflicts on the 3-9 fragment loads per 8 columns, which the measurements below include.  The last slot of a packed row holds |b|^2: the A-side fragment carries 1.0
+// there and -2 a_k elsewhere, the accumulator of the first DMMA starts at |a|^2, and the contraction yields
+// q = |a|^2 + |b|^2 - 2 a.b with no extra FP64 slot.
+//
+//   CTA = 8 warps, warp = 32 rows (4 m-tiles, A fragments in registers for the whole item);
+//   work item = (row block of 256 rows, chunk of 1024 columns), columns at/after the row block only; tiles
+//   overlapping the row block are evaluated as ordered pairs (row sums only), tiles beyond it feed y_i and y_j;
+//   64-column tiles stream through an 8-stage cp.async.bulk/mbarrier ring;
+//   software pipeline over n-tiles (8 columns), across tile boundaries: the DMMAs of n-tile t+1 are issued
+//   before the kernel map of n-tile t;
+//   the warps never synchronise with each other: column sums leave each warp as one coalesced 256-byte RED
+//   per 32 columns (transposing butterfly over the 8 lanes that share a column pair), row sums once per item.
+#pragma once
+#include "kmv_impl.cuh"
+
+namespace cglb {
+
+constexpr int DS_STAGES = 8;                  // 64-column tiles in the ring (4 in flight ahead of warp 0)
+constexpr int DS_RPC = 4;                     // row blocks per column chunk (chunk = 4 x rows per item)
+
+__device__ __forceinline__ void dmma884c(double (&d)[2], double a, double b, double c0, double c1) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+        : "=d"(d[0]), "=d"(d[1])
+        : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+template <int ROWS>
+struct DCursor {
+    static constexpr int DS_ROWS = ROWS, DS_CHUNK = DS_RPC * ROWS;
+    long tau;
+    long r0;        // first row of the row block
+    long c0;        // first column of the first tile
+    int tile, ntiles;
+    bool valid;
+    __device__ __forceinline__ void load_item(const SweepArgs& a, long n_chunks) {
+        for (;; tau += gridDim.x) {
+            const long t = tau * a.nparts + a.part;
+            valid = t < a.nitems;
+            if (!valid) return;
+            // chunk-major enumeration of {(I, C) : I < DS_RPC (C + 1)}: prefix(C) = DS_RPC C (C + 1) / 2
+            long c = (long)((sqrt(1.0 + 8.0 * (double)t / DS_RPC) - 1.0) * 0.5);
+            while (DS_RPC * c * (c + 1) / 2 > t) --c;
+            while (DS_RPC * (c + 1) * (c + 2) / 2 <= t) ++c;
+            const long I = t - DS_RPC * c * (c + 1) / 2;
+            if (I >= a.nb_rows || c >= n_chunks) continue;
+            r0 = I * DS_ROWS;
+            long cbeg = c * DS_CHUNK;
+            if (cbeg < r0) cbeg = r0;
+            long cend = (c + 1) * DS_CHUNK;
+            if (cend > a.ncols) cend = a.ncols;
+            if (cbeg >= cend) continue;
+            c0 = cbeg;
+            ntiles = (int)((cend - cbeg + kBJ - 1) / kBJ);
+            tile = 0;
+            return;
+        }
+    }
+    __device__ __forceinline__ void start(const SweepArgs& a, long n_chunks) { tau = blockIdx.x; load_item(a, n_chunks); }
+    __device__ __forceinline__ void next_tile(const SweepArgs& a, long n_chunks) {
+        if (++tile == ntiles) { tau += gridDim.x; load_item(a, n_chunks); }
+    }
+};
+
+// WARPS warps x MT m-tiles (8 rows each) per warp; lane 0 of warp 0 also drives the TMA ring, as in the
+// register-resident sweep (a dedicated producer warp and 12 / 16-warp shapes were measured and are slower,
+// profiles/README_r02.md)
+template <int KIND, int DP, int WARPS, int MT>
+__global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepArgs args, const long n_chunks) {
+    constexpr int KS = (DP + 3) / 4;    // k-steps; slots DP .. 4 KS - 1 belong to the next packed row (A carries 0 there)
+    constexpr int DS_WARPS = WARPS, DS_THREADS = WARPS * 32, DS_ROWS = WARPS * 8 * MT;
+    constexpr int WROWS = 8 * MT;       // rows per warp
+    using Cur = DCursor<DS_ROWS>;
+    static_assert(DP % 2 == 0 && DP >= 4, "packed row width");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_tab[kExpTabBig];                                  // static: LDS with an immediate base
+    double* s_x = reinterpret_cast<double*>(smem_raw);                    // [DS_STAGES][kBJ*DP]
+    double* s_v = s_x + DS_STAGES * kBJ * DP;                               // [DS_STAGES][kBJ]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_v + DS_STAGES * kBJ);
+    uint64_t* s_empty = s_full + DS_STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int i = tid; i < kExpTabBig; i += DS_THREADS) s_tab[i] = args.exp_tab[kExpTabSmall + i];
+    if (DP % 4 != 0) {
+        // the last k-step of a column reads 2 doubles of the next packed row (times 0 from the A side): every
+        // byte a fragment load can touch must hold a finite number before the first tile lands
+        for (int i = tid; i < DS_STAGES * kBJ * DP + DS_STAGES * kBJ; i += DS_THREADS) s_x[i] = 0.0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < DS_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], DS_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (DP % 4 != 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // zero fill before the TMA writes
+
+    int pstage = 0, stage = 0;
+    uint32_t pphase = 0, phase = 0;
+    auto produce = [&](Cur& pc) {
+        if (!pc.valid) return;
+        mbar_wait(&s_empty[pstage], pphase ^ 1);
+        const long j0 = pc.c0 + (long)pc.tile * kBJ;
+        mbar_expect_tx(&s_full[pstage], (uint32_t)((kBJ * DP + kBJ) * sizeof(double)));
+        tma_load_1d(s_x + pstage * kBJ * DP, args.xp_cols + j0 * DP, kBJ * DP * sizeof(double), &s_full[pstage]);
+        tma_load_1d(s_v + pstage * kBJ, args.vcol + j0, kBJ * sizeof(double), &s_full[pstage]);
+        if (++pstage == DS_STAGES) { pstage = 0; pphase ^= 1; }
+        pc.next_tile(args, n_chunks);
+    };
+
+    Cur cc;
+    cc.start(args, n_chunks);
+    Cur pc = cc;
+    if (tid == 0) {
+#pragma unroll 1
+        for (int i = 0; i < DS_STAGES / 2; ++i) produce(pc);
+    }
+    const double var = args.variance;
+
+    while (cc.valid) {
+        const long r0 = cc.r0;
+        const long c0 = cc.c0;
+        const int ntiles = cc.ntiles;
+        // A fragments: lane (g, t4) holds A[row g + 8 i][4 ks + t4], A = (-2 a_0 .. -2 a_{DP-2}, 1)
+        double af[MT][KS], na[MT], vrow[MT], racc[MT];
+        bool live[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const long row = r0 + warp * WROWS + i * 8 + g;
+            live[i] = row < args.nrows;
+            const double* src = args.xp_rows + (live[i] ? row : 0) * DP;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int k = 4 * ks + t4;
+                const double val = (live[i] && k < DP) ? __ldg(src + k) : 0.0;
+                af[i][ks] = (k == DP - 1) ? 1.0 : -2.0 * val;
+            }
+            na[i] = live[i] ? __ldg(src + DP - 1) : 0.0;
+            vrow[i] = live[i] ? __ldg(args.vcol + row) : 0.0;
+            racc[i] = 0.0;
+        }
+        // One n-tile = 8 columns x the warp's 8 MT rows: KS chained DMMAs per m-tile, started from |a|^2.
+        auto dmma_ntile = [&](const double* sx, int col0, double (&acc)[MT][2]) {
+            double bf[KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) bf[ks] = sx[(col0 + g) * DP + 4 * ks + t4];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                dmma884c(acc[i], af[i][0], bf[0], na[i], na[i]);
+#pragma unroll
+                for (int ks = 1; ks < KS; ++ks) dmma884c(acc[i], af[i][ks], bf[ks], acc[i][0], acc[i][1]);
+            }
+        };
+        // Software pipeline over n-tiles, across tile boundaries: the DMMAs of n-tile t+1 are issued before the
+        // kernel map of n-tile t, so the map always has all 2 MT chains of a full n-tile to interleave.
+        if (tid == 0) produce(pc);
+        __syncwarp();
+        mbar_wait(&s_full[stage], phase);
+        double accn[MT][2];
+        dmma_ntile(s_x + stage * kBJ * DP, 0, accn);
+#pragma unroll 1
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const double* sx = s_x + stage * kBJ * DP;
+            const double* sv = s_v + stage * kBJ;
+            const long j0 = c0 + (long)tile * kBJ;
+            const bool offdiag = j0 >= r0 + DS_ROWS;
+            const int nstage = (stage + 1 == DS_STAGES) ? 0 : stage + 1;
+            const uint32_t nphase = (nstage == 0) ? (phase ^ 1) : phase;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                double c8[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int col0 = half * 32 + j * 8;
+                    double acc[MT][2];
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) { acc[i][0] = accn[i][0]; acc[i][1] = accn[i][1]; }
+                    const double2 vv = *reinterpret_cast<const double2*>(sv + col0 + 2 * t4);
+                    if (j < 3 || half == 0) {
+                        dmma_ntile(sx, col0 + 8, accn);
+                    } else if (tile + 1 < ntiles) {
+                        if (tid == 0) produce(pc);
+                        __syncwarp();
+                        mbar_wait(&s_full[nstage], nphase);
+                        dmma_ntile(s_x + nstage * kBJ * DP, 0, accn);
+                    }
+                    double cs0 = 0.0, cs1 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        const double k0 = kappa<KIND, 10>(acc[i][0], s_tab);
+                        const double k1 = kappa<KIND, 10>(acc[i][1], s_tab);
+                        racc[i] = fma(k0, vv.x, racc[i]);
+                        racc[i] = fma(k1, vv.y, racc[i]);
+                        cs0 = fma(k0, vrow[i], cs0);
+                        cs1 = fma(k1, vrow[i], cs1);
+                    }
+                    c8[2 * j] = cs0;
+                    c8[2 * j + 1] = cs1;
+                }
+                if (offdiag) {
+                    // sum the 8 column partials over the 8 lanes sharing t4 (lane bits 2..4): transposing butterfly
+                    int cnt = 8;
+#pragma unroll
+                    for (int off = 16; off >= 4; off >>= 1, cnt >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int h = 0; h < cnt / 2; ++h) {
+                            const double send = up ? c8[h] : c8[h + cnt / 2];
+                            const double keep = up ? c8[h + cnt / 2] : c8[h];
+                            c8[h] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // = 2 j + e
+                    // every lane now holds one of the 32 column sums of this half tile (over the warp's rows):
+                    // one coalesced 256-byte RED per warp, no cross-warp reduction and no CTA barrier
+                    const long jc = j0 + half * 32 + (idx >> 1) * 8 + 2 * t4 + (idx & 1);
+                    if (jc < args.ncols) atomicAdd(args.y + jc, var * c8[0]);
+                }
+            }
+            // this warp is done with the stage (the first n-tile of the next stage has been read already)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stage]);
+            stage = nstage;
+            phase = nphase;
+        }
+        // row sums: reduce over the 4 lanes sharing g; every warp owns its 32 rows
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            double s = racc[i];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (t4 == 0 && live[i]) atomicAdd(args.y + r0 + warp * WROWS + i * 8 + g, var * s);
+        }
+        cc.tau += gridDim.x;
+        cc.load_item(args, n_chunks);
+    }
+}
+
+static inline size_t dsweep_smem_bytes(int dp) {
+    return (size_t)(DS_STAGES * kBJ * dp + DS_STAGES * kBJ) * sizeof(double) + 2 * DS_STAGES * sizeof(uint64_t);
+}
+
+template <int KIND, int DP, int WARPS = 8, int MT = 4>
+static int run_dsweep(Context* ctx, SweepArgs a, cudaStream_t st) {
+    constexpr int ROWS = WARPS * 8 * MT, CHUNK = DS_RPC * ROWS, THREADS = WARPS * 32;
+    a.nb_rows = (a.nrows + ROWS - 1) / ROWS;
+    const long n_chunks = (a.ncols + CHUNK - 1) / CHUNK;
+    a.nb_cols = n_chunks;
+    a.nitems = DS_RPC * n_chunks * (n_chunks + 1) / 2;
+    auto kern = dmma_sweep_kernel<KIND, DP, WARPS, MT>;
+    const size_t smem = dsweep_smem_bytes(DP);
+    CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
+    if (my_items <= 0) return CGLB_OK;
+    const int grid = (int)(my_items < ctx->num_sms ? my_items : ctx->num_sms);
+    kern<<<grid, THREADS, smem, st>>>(a, n_chunks);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+}  // namespace cglb

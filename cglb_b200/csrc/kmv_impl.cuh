@@ -771,7 +771,7 @@ static int run_bwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
 #endif
 
 // dispatch table filled by the per-D translation units
-typedef int (*sweep_fn)(Context*, int kind, int mode /*0 sym fwd, 1 rect fwd, 2 sym bwd*/, const SweepArgs&, cudaStream_t);
+typedef int (*sweep_fn)(Context*, int kind, int mode /*0 sym fwd, 1 rect fwd, 2 sym bwd, 3 sym fwd on DMMA*/, const SweepArgs&, cudaStream_t);
 typedef int (*knm_fn)(Context*, int kind, int bwd, const KnmArgs&, cudaStream_t);
 knm_fn get_knm_fn(int d);
 constexpr int kMaxRegisterD = 32;

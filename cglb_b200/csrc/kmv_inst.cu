@@ -1,6 +1,7 @@
 // One translation unit per input dimension D (compiled with -DCGLB_KMV_D=<d>), so the 16 x 2 x 8
 // template instantiations of the sweeps build in parallel.
 #include "kmv_impl.cuh"
+#include "dsweep_impl.cuh"
 
 #ifndef CGLB_KMV_D
 #error "compile with -DCGLB_KMV_D=<d>"
@@ -13,6 +14,15 @@ namespace cglb {
 
 int CGLB_CAT(sweep_d, CGLB_KMV_D)(Context* ctx, int kind, int mode, const SweepArgs& a, cudaStream_t st) {
     constexpr int D = CGLB_KMV_D;
+    if (mode == 3) {      // symmetric forward sweep with the distance contraction on DMMA (dsweep_impl.cuh)
+        if constexpr (D >= 2) {
+            constexpr int DP = SmemLayout<D>::DP;
+            return kind == CGLB_MATERN32 ? run_dsweep<CGLB_MATERN32, DP>(ctx, a, st) : run_dsweep<CGLB_RBF, DP>(ctx, a, st);
+        } else {
+            set_error("dsweep: d=%d is not instantiated", D);
+            return CGLB_ERR_UNSUPPORTED;
+        }
+    }
     if (kind == CGLB_MATERN32) {
         if (mode == 0) return run_fwd<CGLB_MATERN32, D, true>(ctx, a, st);
         if (mode == 1) return run_fwd<CGLB_MATERN32, D, false>(ctx, a, st);

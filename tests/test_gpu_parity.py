@@ -54,7 +54,7 @@ def test_kmv_sym_matches_oracle(eng, kind, n, d):
     assert float((parts.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
 
 
-# ---- K1 on DMMA (dsweep.cu): the path the n >= 24k, d in {10, 11, 18, 19, 26, 27} sweeps take -------------------------
+# ---- K1 on DMMA (dsweep_impl.cuh): the path the n >= 24k, 10 <= d <= 32 sweeps take -------------------------
 @pytest.mark.parametrize("kind,n,d,lsval", [("matern32", 1, 11, None), ("matern32", 257, 11, None), ("matern32", 2500, 11, None),
                                             ("rbf", 1500, 10, 2.0), ("matern32", 3333, 19, 2.0), ("rbf", 1111, 27, 3.0),
                                             ("rbf", 1300, 18, None), ("matern32", 900, 26, None), ("matern32", 1300, 2, 0.7),
@@ -75,6 +75,21 @@ def test_dmma_sweep_matches_oracle(eng, monkeypatch, kind, n, d, lsval):
     y0 = eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.3, 0.07)
     # both are expanded-form kernels: at the tiny-lengthscale case their cancellation errors (|a|^2 ~ 1e5) differ
     assert float((y - y0).norm() / y0.norm()) <= (1e-12 if lsval is None else 1e-11)
+
+
+@pytest.mark.parametrize("d", list(range(2, 33)))
+def test_dmma_sweep_every_dimension(eng, monkeypatch, d):
+    """every packed width: multiples of 4, widths whose last k-step reads into the next packed row (d = 12, 13,
+    16, 17 ...), ragged n (last tile and last row block partly empty)."""
+    monkeypatch.setenv("CGLB_DSWEEP", "2")
+    kind = "matern32" if d % 2 else "rbf"
+    n = 700 + 13 * d
+    x, v, u, ls = _problem(n, d, seed=100 + d)
+    dev = eng.device
+    xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    ref = o.kernel_dense(kind, x, x, ls, torch.tensor(0.9, dtype=f64)) @ v + 0.3 * v
+    y = eng.kmv_sym(kind, xp, n, d, v.to(dev), 0.9, 0.3)
+    assert float((y.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
 
 
 def test_dmma_sweep_duplicates_and_midsize(eng, monkeypatch):
