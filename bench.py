@@ -302,6 +302,9 @@ def run_b200(args, rank, world, local_rank):
     achieved = fpp * float(n) * n / world / (kmv_ms * 1e-3) / 1e12 if n_kmv else None
     ncu = load_json(os.path.join(ROOT, "profiles", "kmv_ncu_summary.json")) or {}
     traffic = ncu.get(f"{args.workload}", {}).get("dram_bytes_per_launch")
+    variant = eng.kmv_sym_variant(d, n, world)
+    diag_block = {0: 1024.0, 1: 256.0, 2: 128.0}[variant]      # rows of the diagonal blocks, evaluated as full squares
+    eval_frac = 0.5 + 0.5 * min(1.0, diag_block / n)
     n_pre = ksum.get("precond_project", (0, 0.0))[0]
     pre_bytes = 2.0 * M * (n / world) * 8 + 4.0 * (n / world) * 8
     pre_ms = float(kt[2]) / max(n_pre, 1)
@@ -320,7 +323,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": ms_e2e * 1e-3, "unit": "s/step", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": int(lt.item()),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "kmv_sweep_kernel (K1, symmetric matrix-free K*v)",
+        "roofline": {"bound": "tensor", "kernel": "K1 symmetric matrix-free K*v: " + eng.KMV_VARIANTS[variant],
                      "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if achieved else None,
                      "traffic": traffic,
                      "note": "algorithmic-FLOP fraction: (3d+7) n^2 FLOP per K*v (SURVEY.md 8d) / CUDA-event time per launch; "
@@ -328,9 +331,9 @@ def run_b200(args, rank, world, local_rank):
                              "(profiles/fp64_peaks_r01.json, 'of measured'); the symmetric sweep evaluates each unordered pair once, so `achieved` "
                              "(nominal n^2 pairs of the reference's K*v) can exceed the peak; `achieved_evaluated` counts only the pairs "
                              "actually evaluated (n^2/2 + the diagonal blocks)",
-                     "achieved_evaluated": (achieved * (0.5 + 0.5 * min(1.0, (1024.0 if d <= 32 else 128.0) / n))) if achieved else None,
-                     "frac_evaluated": (achieved * (0.5 + 0.5 * min(1.0, (1024.0 if d <= 32 else 128.0) / n)) / fp64_peak) if achieved else None,
-                     "fp64_pipe_utilisation_ncu": ncu.get("fp64_pipe_active_pct"),
+                     "achieved_evaluated": (achieved * eval_frac) if achieved else None,
+                     "frac_evaluated": (achieved * eval_frac / fp64_peak) if achieved else None,
+                     "fp64_pipe_utilisation_ncu": (ncu.get("fp64_pipe_active_pct_by_variant") or {}).get(str(variant), ncu.get("fp64_pipe_active_pct")),
                      "launches": n_kmv, "ms_per_launch": kmv_ms,
                      "share_of_step": float(kt[0]) / float(t_dev[0]) if float(t_dev[0]) else None},
         "roofline_other": {

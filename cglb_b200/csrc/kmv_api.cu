@@ -165,6 +165,14 @@ extern "C" int cglb_pack_inputs(cglb_context* c, int kind, const double* x, long
     return CGLB_OK;
 }
 
+extern "C" int cglb_kmv_sym_variant(const cglb_context* c, int d, long n, int nparts) {
+    const Context* ctx = reinterpret_cast<const Context*>(c);
+    if (!ctx || d < 1 || n < 0 || nparts < 1) return CGLB_ERR_ARG;
+    if (d > CGLB_MAX_REGISTER_D) return 2;
+    const int dm = dsweep_mode();
+    return (dm != 0 && dsweep_supported(ctx, d, n, dm == 2 ? 0 : nparts)) ? 1 : 0;
+}
+
 extern "C" int cglb_kmv_sym(cglb_context* c, int kind, const double* xp, long n, int d, const double* v, double* y,
                             double variance, double diag, int part, int nparts, void* stream) {
     Context* ctx = reinterpret_cast<Context*>(c);

@@ -114,6 +114,13 @@ class Engine:
         return out
 
     # ---- K1 / K2 ------------------------------------------------------------------------------------
+    KMV_VARIANTS = {0: "kmv_sweep_kernel (register-resident DFMA sweep)", 1: "dmma_sweep_kernel (DMMA-distance sweep, d <= 32)",
+                    2: "wide_sweep_kernel (DMMA sweep, d > 32)"}
+
+    def kmv_sym_variant(self, d: int, n: int, nparts: int = 1) -> int:
+        """which kernel cglb_kmv_sym launches for this shape (include/cglb_b200.h)"""
+        return int(self.lib.cglb_kmv_sym_variant(self.ctx, int(d), int(n), int(nparts)))
+
     def kmv_sym(self, kind, xp, n, d, v, variance, diag, out=None, part=0, nparts=1) -> Tensor:
         _req(xp, "xp"); _req(v, "v")
         if out is None:

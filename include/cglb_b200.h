@@ -74,6 +74,11 @@ CGLB_API int cglb_pack_inputs(cglb_context* ctx, int kind, const double* x, long
 CGLB_API int cglb_kmv_sym(cglb_context* ctx, int kind, const double* xp, long n, int d, const double* v, double* y,
                  double variance, double diag, int part, int nparts, void* stream);
 
+/* Which kernel cglb_kmv_sym launches for this shape: 0 = register-resident DFMA sweep (kmv_impl.cuh),
+ * 1 = DMMA-distance sweep for 10 <= d <= 32 (dsweep_impl.cuh), 2 = wide DMMA sweep for d > 32 (widek.cu).
+ * Pure query (no launch); benchmarks use it to name the kernel they time. */
+CGLB_API int cglb_kmv_sym_variant(const cglb_context* ctx, int d, long n, int nparts);
+
 /* y[0:nrows] = variance * K(rows, cols) v[0:ncols]   (rectangular, e.g. K_sf v of PredictCG)
  * replaces: `ksf @ new_v` at cglb/backend/pytorch/models.py:334 */
 CGLB_API int cglb_kmv_rect(cglb_context* ctx, int kind, const double* xp_rows, long nrows, const double* xp_cols,
