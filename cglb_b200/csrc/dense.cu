@@ -358,12 +358,117 @@ constexpr int DP1 = NB + 1;
 
 // mode 0: factor the block (a <- L, upper zeroed) and write inv(L) to dinv; mode 1: block already
 // holds L (lower), only invert.  nb_actual = rows in this block (<= NB).  info: 1+block on failure.
-__global__ void __launch_bounds__(1024, 1) diag_block_kernel(double* a, long lda, long m, long first_block,
-                                                            double* dinv_base, int mode, int* info) {
+//
+// Register-tiled: 256 threads form a 16 x 16 grid, thread (ty, tx) owns the 8 x 8 elements
+// (i, k) = (ty + 16 a, tx + 16 b) of the working matrix in registers.  Each of the 128 column steps costs ONE
+// CTA barrier: the owners of column j publish it (unscaled) in shared memory, everybody derives 1/pivot
+// redundantly and updates its own registers (right-looking); the loops over the 16-column groups are unrolled
+// so that finished register tiles drop out statically.  The inverse is a forward substitution on the identity
+// with the same ownership (B in registers, row j of X published per step).  The first version kept the matrix
+// in shared memory (5 barriers + dependent read-modify-write chains per column, 1024 threads: 212 us per
+// block); with 8 warps the per-column instruction overhead is paid 8 times instead of 32.
+constexpr int DG = 16;               // thread grid is DG x DG, register tile is (NB/DG) x (NB/DG)
+constexpr int DT = NB / DG;          // 8
+
+__device__ __forceinline__ double rsqrt_full(double d) {
+    // MUFU.RSQ64H seed (2^-20) + one third-order and one Newton step: full fp64 accuracy
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d * y, y, 1.0);
+    y = fma(y * fma(e, 0.375, 0.5), e, y);
+    e = fma(-d * y, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+
+// Cholesky steps j = 16 JB .. 16 JB + 15
+template <int JB>
+__device__ __forceinline__ void chol_group(double (&r)[DT][DT], double* s, double* sr, double* buf, int ty, int tx, int* s_fail) {
+#pragma unroll 1
+    for (int jx = 0; jx < DG; ++jx) {
+        const int j = JB * DG + jx;
+        double* col = buf + (j & 1) * NB;
+        if (tx == jx) {      // owners of column j publish rows ty + 16 a (a >= JB holds the rows >= 16 JB)
+#pragma unroll
+            for (int aa = JB; aa < DT; ++aa) col[ty + DG * aa] = r[aa][JB];
+        }
+        __syncthreads();
+        double d = col[j];
+        if (!(d > 0.0)) {
+            *s_fail = 1;
+            d = 1.0;
+        }
+        const double rinv = rsqrt_full(d);
+        const double dinv = rinv * rinv;
+        double ci[DT], ck[DT];
+#pragma unroll
+        for (int aa = JB; aa < DT; ++aa) ci[aa] = col[ty + DG * aa] * dinv;      // a_ij / d
+#pragma unroll
+        for (int bb = JB; bb < DT; ++bb) ck[bb] = col[tx + DG * bb];             // a_kj
+        // trailing update r[i][k] -= a_ij a_kj / d for j < k <= i
+#pragma unroll
+        for (int bb = JB; bb < DT; ++bb)
+#pragma unroll
+            for (int aa = bb; aa < DT; ++aa) {
+                bool on = true;
+                if (bb == JB) on = on && (tx > jx);
+                if (aa == bb) on = on && (tx <= ty);
+                if (on) r[aa][bb] = fma(-ci[aa], ck[bb], r[aa][bb]);
+            }
+        if (tx == jx) {      // column j of L is final: l_ij = a_ij / sqrt(d), l_jj = sqrt(d)
+#pragma unroll
+            for (int aa = JB; aa < DT; ++aa) {
+                const int i = ty + DG * aa;
+                if (i > j) s[i * DP1 + j] = col[i] * rinv;
+                else if (i == j) {
+                    double sq = d * rinv;
+                    s[i * DP1 + j] = fma(fma(-sq, sq, d), 0.5 * rinv, sq);      // sqrt(d), one correction
+                    sr[j] = rinv;
+                }
+            }
+        }
+    }
+}
+
+// forward-substitution steps j = 16 JB .. 16 JB + 15 of X = L^-1
+template <int JB>
+__device__ __forceinline__ void inv_group(double (&bm)[DT][DT], const double* s, const double* sr, double* buf, int ty, int tx) {
+#pragma unroll 1
+    for (int jx = 0; jx < DG; ++jx) {
+        const int j = JB * DG + jx;
+        double* row = buf + (j & 1) * NB;
+        if (ty == jx) {      // owners of row j: X[j][c] = B[j][c] / L[j][j], final; columns c <= j live in b <= JB
+            const double rinv = sr[j];
+#pragma unroll
+            for (int bb = 0; bb <= JB; ++bb) {
+                bm[JB][bb] *= rinv;
+                row[tx + DG * bb] = bm[JB][bb];
+            }
+        }
+        __syncthreads();
+        double lj[DT], xj[DT];
+#pragma unroll
+        for (int aa = JB; aa < DT; ++aa) lj[aa] = s[(ty + DG * aa) * DP1 + j];
+#pragma unroll
+        for (int bb = 0; bb <= JB; ++bb) xj[bb] = row[tx + DG * bb];
+        // B[i][c] -= L[i][j] X[j][c] for i > j, c <= j
+#pragma unroll
+        for (int aa = JB; aa < DT; ++aa)
+#pragma unroll
+            for (int bb = 0; bb <= JB; ++bb) {
+                bool on = true;
+                if (aa == JB) on = on && (ty > jx);
+                if (bb == JB) on = on && (tx <= jx);
+                if (on) bm[aa][bb] = fma(-lj[aa], xj[bb], bm[aa][bb]);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(DG * DG, 1) diag_block_kernel(double* a, long lda, long m, long first_block,
+                                                               double* dinv_base, int mode, int* info) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* s = reinterpret_cast<double*>(smem_raw);      // [NB][DP1]
-    double* sd = s + NB * DP1;                            // diagonal of L
-    double* sr = sd + NB;                                 // reciprocal diagonal
+    double* s = reinterpret_cast<double*>(smem_raw);      // [NB][DP1]: L (lower incl. diagonal) once known
+    double* sr = s + NB * DP1;                            // [NB] reciprocal diagonal of L
+    double* buf = sr + NB;                                // [2][NB] published column (Cholesky) / row (inverse) of a step
     __shared__ int s_fail;
     const long blk = first_block + blockIdx.x;
     const long r0 = blk * NB;
@@ -371,93 +476,79 @@ __global__ void __launch_bounds__(1024, 1) diag_block_kernel(double* a, long lda
     double* ablk = a + r0 * lda + r0;
     double* dinv = dinv_base + blk * (long)NB * NB;
     const int tid = threadIdx.x;
-    const int ty = tid >> 5, tx = tid & 31;      // 32 x 32 thread grid: the loops are latency-bound, TLP hides it
+    const int ty = tid / DG, tx = tid % DG;
     if (tid == 0) s_fail = 0;
-    // load lower triangle (incl. diag); pad with identity
-    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-        const int i = idx / NB, j = idx % NB;
-        double v = 0.0;
-        if (i < nb && j < nb && j <= i) v = ablk[(long)i * lda + j];
-        if (i >= nb && i == j) v = 1.0;
-        s[i * DP1 + j] = v;
-    }
-    __syncthreads();
+
     if (mode == 0) {
-        // right-looking unblocked Cholesky on the lower triangle
-        for (int j = 0; j < NB; ++j) {
-            if (tid == 0) {
-                double d = s[j * DP1 + j];
-                if (!(d > 0.0)) { s_fail = 1; d = 1.0; }
-                // 1/sqrt(d): MUFU.RSQ64H seed + Newton steps (full fp64 accuracy), sqrt = d * rsqrt + one correction
-                double y;
-                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-                double e = fma(-d * y, y, 1.0);
-                y = fma(y * fma(e, 0.375, 0.5), e, y);
-                e = fma(-d * y, y, 1.0);
-                y = fma(0.5 * y, e, y);
-                double sq = d * y;
-                sq = fma(fma(-sq, sq, d), 0.5 * y, sq);
-                sd[j] = sq;
-                sr[j] = y;
+        // working matrix in registers: lower triangle of the block, identity padding beyond nb
+        double r[DT][DT];
+#pragma unroll
+        for (int aa = 0; aa < DT; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < DT; ++bb) {
+                const int i = ty + DG * aa, k = tx + DG * bb;
+                double v = 0.0;
+                if (i < nb && k <= i) v = ablk[(long)i * lda + k];
+                if (i >= nb && i == k) v = 1.0;
+                r[aa][bb] = v;
             }
-            __syncthreads();
-            const double rinv = sr[j];
-            for (int i = j + 1 + tid; i < NB; i += blockDim.x) s[i * DP1 + j] *= rinv;
-            __syncthreads();
-            // trailing update: s[i][k] -= s[i][j] * s[k][j] for j < k <= i   (32 x 32 thread grid)
-            for (int i = j + 1 + ty; i < NB; i += 32) {
-                const double lij = s[i * DP1 + j];
-                for (int k = j + 1 + tx; k <= i; k += 32) s[i * DP1 + k] = fma(-lij, s[k * DP1 + j], s[i * DP1 + k]);
-            }
-            __syncthreads();
-        }
+        __syncthreads();
+        chol_group<0>(r, s, sr, buf, ty, tx, &s_fail);
+        chol_group<1>(r, s, sr, buf, ty, tx, &s_fail);
+        chol_group<2>(r, s, sr, buf, ty, tx, &s_fail);
+        chol_group<3>(r, s, sr, buf, ty, tx, &s_fail);
+        chol_group<4>(r, s, sr, buf, ty, tx, &s_fail);
+        chol_group<5>(r, s, sr, buf, ty, tx, &s_fail);
+        chol_group<6>(r, s, sr, buf, ty, tx, &s_fail);
+        chol_group<7>(r, s, sr, buf, ty, tx, &s_fail);
+        __syncthreads();
         // write L back, zero the upper triangle of the block
         for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
             const int i = idx / nb, j = idx % nb;
-            double v = (j < i) ? s[i * DP1 + j] : (j == i ? sd[i] : 0.0);
-            ablk[(long)i * lda + j] = v;
+            ablk[(long)i * lda + j] = (j <= i) ? s[i * DP1 + j] : 0.0;
         }
         if (tid == 0 && s_fail) atomicCAS(info, 0, (int)(blk + 1));
     } else {
-        for (int i = tid; i < NB; i += blockDim.x) {
-            double d = s[i * DP1 + i];
-            sd[i] = d;
-            sr[i] = 1.0 / d;
-        }
-    }
-    __syncthreads();
-    // inverse X = L^-1 stored transposed in the upper triangle: XT[c][j] = X[j][c]  (c <= j).
-    // right-looking forward substitution on all columns at once; working RHS B starts as identity.
-    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-        const int c = idx / NB, j = idx % NB;
-        if (j >= c) s[c * DP1 + j] = (j == c) ? 1.0 : 0.0;     // (diag of L is in sd, safe to overwrite)
-    }
-    __syncthreads();
-    for (int j = 0; j < NB; ++j) {
-        // X[j][c] = B[j][c] / L[j][j] for c <= j
-        const double rinv = sr[j];
-        for (int c = tid; c <= j; c += blockDim.x) s[c * DP1 + j] *= rinv;
-        __syncthreads();
-        // B[i][c] -= L[i][j] * X[j][c] for i > j, c <= j
-        for (int c = ty; c <= j; c += 32) {
-            const double xjc = s[c * DP1 + j];
-            for (int i = j + 1 + tx; i < NB; i += 32) s[c * DP1 + i] = fma(-s[i * DP1 + j], xjc, s[c * DP1 + i]);
+        for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
+            const int i = idx / NB, j = idx % NB;
+            double v = 0.0;
+            if (i < nb && j <= i) v = ablk[(long)i * lda + j];
+            if (i >= nb && i == j) v = 1.0;
+            s[i * DP1 + j] = v;
+            if (i == j) sr[i] = 1.0 / v;
         }
         __syncthreads();
     }
-    for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-        const int i = idx / NB, c = idx % NB;
-        dinv[idx] = (c <= i) ? s[c * DP1 + i] : 0.0;
-    }
+    // inverse X = L^-1 by forward substitution on the identity, B in registers (same ownership)
+    double bm[DT][DT];
+#pragma unroll
+    for (int aa = 0; aa < DT; ++aa)
+#pragma unroll
+        for (int bb = 0; bb < DT; ++bb) bm[aa][bb] = (ty + DG * aa == tx + DG * bb) ? 1.0 : 0.0;
+    inv_group<0>(bm, s, sr, buf, ty, tx);
+    inv_group<1>(bm, s, sr, buf, ty, tx);
+    inv_group<2>(bm, s, sr, buf, ty, tx);
+    inv_group<3>(bm, s, sr, buf, ty, tx);
+    inv_group<4>(bm, s, sr, buf, ty, tx);
+    inv_group<5>(bm, s, sr, buf, ty, tx);
+    inv_group<6>(bm, s, sr, buf, ty, tx);
+    inv_group<7>(bm, s, sr, buf, ty, tx);
+#pragma unroll
+    for (int aa = 0; aa < DT; ++aa)
+#pragma unroll
+        for (int bb = 0; bb < DT; ++bb) {
+            const int i = ty + DG * aa, c = tx + DG * bb;
+            dinv[i * NB + c] = (c <= i) ? bm[aa][bb] : 0.0;
+        }
 }
 
-static size_t diag_smem_bytes() { return (size_t)(NB * DP1 + 2 * NB) * sizeof(double); }
+static size_t diag_smem_bytes() { return (size_t)(NB * DP1 + 3 * NB) * sizeof(double); }
 
 static int launch_diag(Context* ctx, double* a, long lda, long m, long first_block, long nblocks, double* dinv, int mode,
                        int* info, cudaStream_t st) {
     size_t smem = diag_smem_bytes();
     CGLB_CUDA_OK(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    diag_block_kernel<<<(unsigned)nblocks, 1024, smem, st>>>(a, lda, m, first_block, dinv, mode, info);
+    diag_block_kernel<<<(unsigned)nblocks, DG * DG, smem, st>>>(a, lda, m, first_block, dinv, mode, info);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;
