@@ -30,17 +30,19 @@ Tensor = torch.Tensor
 class ShardedKernelMatvec:
     """(variance K(X,X) + sigma^2 I) @ v over this rank's share of the symmetric work items + all-reduce."""
 
-    def __init__(self, eng, kind, xp, n, d, variance, diag, shard: Shard):
+    def __init__(self, eng, kind, xp, n, d, variance, diag, shard: Shard, xpf=None):
         self.eng, self.kind, self.xp, self.n, self.d = eng, kind, xp, n, d
         self.variance, self.diag, self.shard = float(variance), float(diag), shard
+        self.xpf = xpf          # fp32 packed inputs: kernel pairs evaluated in FP32 (fp32 models), else None
         self.count = 0
 
     def detach(self):
         return self
 
     def __matmul__(self, v: Tensor) -> Tensor:
-        y = self.eng.kmv_sym(self.kind, self.xp, self.n, self.d, v.detach().reshape(-1).contiguous(), self.variance, self.diag,
-                             part=self.shard.rank, nparts=self.shard.world)
+        sweep = self.eng.kmv_sym if self.xpf is None else self.eng.kmv_sym_f32
+        y = sweep(self.kind, self.xp if self.xpf is None else self.xpf, self.n, self.d, v.detach().reshape(-1).contiguous(),
+                  self.variance, self.diag, part=self.shard.rank, nparts=self.shard.world)
         self.shard.all_reduce(y)
         self.count += 1
         return y.reshape(v.shape)
@@ -71,7 +73,11 @@ class BoundOutput:
 
 
 class BoundEvaluator:
-    def __init__(self, x: Tensor, y: Tensor, shard: Optional[Shard] = None):
+    def __init__(self, x: Tensor, y: Tensor, shard: Optional[Shard] = None, pair_dtype: str = "f64"):
+        """pair_dtype "f32": the n^2 kernel-pair evaluations of the K*v sweeps run in FP32 (the reference's fp32
+        switch, interface.py:96-110); inputs, accumulation and everything M-sized stay FP64."""
+        if pair_dtype not in ("f64", "f32"):
+            raise CglbError(f"pair_dtype must be 'f64' or 'f32', got {pair_dtype!r}")
         if not x.is_cuda:
             raise CglbError("BoundEvaluator needs CUDA tensors (cglb_b200 has no CPU fallback)")
         if x.dtype != torch.float64:
@@ -87,6 +93,9 @@ class BoundEvaluator:
         self.ld = max(16, (self.ncols + 15) // 16 * 16)
         self.dp = self.eng.packed_width(self.d)
         self.xp = self.eng.empty(self.eng.padded_rows(self.n), self.dp)
+        # fp32-pair mode exists for the register-resident dimensions only; wider inputs keep the FP64 DMMA sweep
+        self.pair_dtype = pair_dtype if self.d <= 32 else "f64"
+        self.xpf = None
         self._A = None
         self._T = None
         self.terms: Optional[CommonTermsDev] = None
@@ -108,6 +117,8 @@ class BoundEvaluator:
 
     def pack(self, kind: str, lengthscale: Tensor):
         self.eng.pack(kind, self.x, lengthscale, self.shift, out=self.xp)
+        if self.pair_dtype == "f32":
+            self.xpf = self.eng.pack_f32(kind, self.x, lengthscale, self.shift, out=self.xpf)
 
     def common_terms(self, kind: str, Z: Tensor, lengthscale: Tensor, variance: float, noise: float, jitter: float) -> CommonTermsDev:
         """models.py:176-213."""
@@ -139,7 +150,8 @@ class BoundEvaluator:
         return NystromPreconditioner(terms.A, terms.LB, noise, shard=self.shard, cols=(self.lo, self.hi), lbinv=terms.LBinv)
 
     def operator(self, kind: str, variance: float, noise: float) -> ShardedKernelMatvec:
-        return ShardedKernelMatvec(self.eng, kind, self.xp, self.n, self.d, variance, noise, self.shard)
+        return ShardedKernelMatvec(self.eng, kind, self.xp, self.n, self.d, variance, noise, self.shard,
+                                   xpf=self.xpf if self.pair_dtype == "f32" else None)
 
     # ------------------------------------------------------------------------------------------------
     def evaluate(self, kind: str, Z: Tensor, lengthscale: Tensor, variance: float, noise: float, mean_c: float,

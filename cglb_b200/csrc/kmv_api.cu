@@ -2,6 +2,7 @@
 #include <stdlib.h>
 
 #include "kmv_impl.cuh"
+#include "f32sweep_impl.cuh"
 
 namespace cglb {
 
@@ -24,6 +25,36 @@ __global__ void pack_inputs_kernel(int kind, const double* __restrict__ x, long 
     }
     for (int k = d; k < dp; ++k) o[k] = 0.0;
     o[norm_index(d)] = nrm;
+}
+
+// fp32 packed layout of the fp32-pair sweeps (f32sweep_impl.cuh): coordinates scaled in fp64, rounded to float;
+// the squared norm is that of the ROUNDED coordinates (the expanded form needs |a|^2 consistent with a)
+__global__ void pack_inputs_f32_kernel(int kind, const double* __restrict__ x, long n, long n_pad, int d, int dpf,
+                                       const double* __restrict__ ls, const double* __restrict__ shift, float* __restrict__ xp) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    float* o = xp + i * dpf;
+    if (i >= n) {
+        for (int k = 0; k < dpf; ++k) o[k] = 0.0f;
+        return;
+    }
+    const double c = (kind == CGLB_MATERN32) ? 1.7320508075688772935 : 0.70710678118654752440;
+    double nrm = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const float a = (float)(c * (x[i * d + k] - (shift ? shift[k] : 0.0)) / ls[k]);
+        o[k] = a;
+        nrm = fma((double)a, (double)a, nrm);
+    }
+    for (int k = d; k < dpf; ++k) o[k] = 0.0f;
+    o[dpf - 1] = (float)nrm;
+}
+
+// vpad32 = float([v, 0...]); y = diag * v
+__global__ void kmv_prologue_f32_kernel(const double* __restrict__ v, long n, long n_pad, float* __restrict__ vpad,
+                                        double* __restrict__ y, double diag) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) vpad[i] = (i < n) ? (float)v[i] : 0.0f;
+    if (i < n) y[i] = diag * v[i];
 }
 
 // vpad = [v, 0...]; y = diag * v (or 0)
@@ -78,6 +109,7 @@ __global__ void bwd_epilogue_kernel(const double* __restrict__ xp, long n, int d
 #endif
 #define X(DD)                                                              \
     int sweep_d##DD(Context*, int, int, const SweepArgs&, cudaStream_t);   \
+    int f32_d##DD(Context*, int, const SweepArgsF32&, cudaStream_t);       \
     int knm_d##DD(Context*, int, int, const KnmArgs&, cudaStream_t);
 CGLB_KMV_DIMS_LIST
 #undef X
@@ -87,6 +119,18 @@ knm_fn get_knm_fn(int d) {
 #define X(DD) \
     case DD:  \
         return knm_d##DD;
+        CGLB_KMV_DIMS_LIST
+#undef X
+        default:
+            return nullptr;
+    }
+}
+
+f32_fn get_f32_fn(int d) {
+    switch (d) {
+#define X(DD) \
+    case DD:  \
+        return f32_d##DD;
         CGLB_KMV_DIMS_LIST
 #undef X
         default:
@@ -163,6 +207,49 @@ extern "C" int cglb_pack_inputs(cglb_context* c, int kind, const double* x, long
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;
+}
+
+extern "C" int cglb_packed_width_f32(int d) { return packed_width_f32(d); }
+
+extern "C" int cglb_pack_inputs_f32(cglb_context* c, int kind, const double* x, long n, int d, const double* lengthscale,
+                                    const double* shift, float* xpf, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && x && lengthscale && xpf, "null pointer");
+    CGLB_CHECK_ARG(n >= 0 && d >= 1, "n >= 0, d >= 1");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    const long n_pad = padded_rows(n);
+    if (n_pad == 0) return CGLB_OK;
+    pack_inputs_f32_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, x, n, n_pad, d, packed_width_f32(d),
+                                                                                             lengthscale, shift, xpf);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+extern "C" int cglb_kmv_sym_f32(cglb_context* c, int kind, const float* xpf, long n, int d, const double* v, double* y,
+                                double variance, double diag, int part, int nparts, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx != nullptr, "null context");
+    CGLB_CHECK_ARG(nparts >= 1 && part >= 0 && part < nparts, "part/nparts");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    if (n == 0) return CGLB_OK;
+    CGLB_CHECK_ARG(xpf && v && y, "null pointer");
+    f32_fn f = d <= CGLB_MAX_REGISTER_D ? get_f32_fn(d) : nullptr;
+    if (!f) {
+        set_error("fp32-pair sweep: d=%d is not instantiated (d <= %d only; use cglb_kmv_sym)", d, CGLB_MAX_REGISTER_D);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long v_pad = (n + 2047) / 2048 * 2048;          // rows are read in blocks of up to 2048
+    int rc = ensure_vpad(ctx, v_pad);                     // the float copy of v lives in the (double) u workspace
+    if (rc) return rc;
+    float* vpad32 = reinterpret_cast<float*>(ctx->upad);
+    kmv_prologue_f32_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(v, n, v_pad, vpad32, y, part == 0 ? diag : 0.0);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    SweepArgsF32 a{};
+    a.xp = xpf; a.vcol = vpad32; a.y = y; a.n = n; a.variance = variance; a.part = part; a.nparts = nparts;
+    return f(ctx, kind, a, st);
 }
 
 extern "C" int cglb_kmv_sym_variant(const cglb_context* c, int d, long n, int nparts) {

@@ -2,6 +2,7 @@
 // template instantiations of the sweeps build in parallel.
 #include "kmv_impl.cuh"
 #include "dsweep_impl.cuh"
+#include "f32sweep_impl.cuh"
 
 #ifndef CGLB_KMV_D
 #error "compile with -DCGLB_KMV_D=<d>"
@@ -34,6 +35,11 @@ int CGLB_CAT(sweep_d, CGLB_KMV_D)(Context* ctx, int kind, int mode, const SweepA
     }
 }
 
+
+int CGLB_CAT(f32_d, CGLB_KMV_D)(Context* ctx, int kind, const SweepArgsF32& a, cudaStream_t st) {
+    constexpr int D = CGLB_KMV_D;
+    return kind == CGLB_MATERN32 ? run_f32<CGLB_MATERN32, D>(ctx, a, st) : run_f32<CGLB_RBF, D>(ctx, a, st);
+}
 
 int CGLB_CAT(knm_d, CGLB_KMV_D)(Context* ctx, int kind, int bwd, const KnmArgs& a, cudaStream_t st) {
     constexpr int D = CGLB_KMV_D;

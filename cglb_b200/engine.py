@@ -130,6 +130,25 @@ class Engine:
             self.stream()), "cglb_kmv_sym"))
         return out
 
+    # ---- fp32-pair mode (models created under set_default_float("fp32")) --------------------------------
+    def pack_f32(self, kind: str, x: Tensor, lengthscale: Tensor, shift: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
+        _req(x, "x"); _req(lengthscale, "lengthscale")
+        n, d = x.shape
+        if out is None:
+            out = self.empty(self.padded_rows(n), int(self.lib.cglb_packed_width_f32(d)), dtype=torch.float32)
+        check(self.lib.cglb_pack_inputs_f32(self.ctx, KIND_IDS[kind], ptr(x), n, d, ptr(lengthscale),
+                                            ptr(shift) if shift is not None else None, ptr(out), self.stream()), "cglb_pack_inputs_f32")
+        return out
+
+    def kmv_sym_f32(self, kind, xpf, n, d, v, variance, diag, out=None, part=0, nparts=1) -> Tensor:
+        _req(xpf, "xpf", torch.float32); _req(v, "v")
+        if out is None:
+            out = self.empty(n)
+        self._timed("kmv_sym", lambda: check(self.lib.cglb_kmv_sym_f32(
+            self.ctx, KIND_IDS[kind], ptr(xpf), n, d, ptr(v), ptr(out), float(variance), float(diag), int(part), int(nparts),
+            self.stream()), "cglb_kmv_sym_f32"))
+        return out
+
     def kmv_rect(self, kind, xp_rows, nrows, xp_cols, ncols, d, v, variance, out=None) -> Tensor:
         _req(xp_rows, "xp_rows"); _req(xp_cols, "xp_cols"); _req(v, "v")
         if out is None:

@@ -183,7 +183,9 @@ class LowerBoundCG(nn.Module):
         if self._evaluator is None or self._evaluator_key != key:
             if not x.is_cuda:
                 raise CglbError("LowerBoundCG needs CUDA tensors: cglb_b200 has no CPU fallback")
-            self._evaluator = BoundEvaluator(x.to(torch.float64), y.to(torch.float64), self._shard)
+            # fp32 models (set_default_float("fp32")): kernel pairs in FP32, everything else promoted to FP64
+            self._evaluator = BoundEvaluator(x.to(torch.float64), y.to(torch.float64), self._shard,
+                                             pair_dtype="f32" if x.dtype == torch.float32 else "f64")
             self._evaluator_key, self._evaluator_version = key, version
         elif self._evaluator_version != version:
             # same buffers, new contents (e.g. a fresh host->device copy): keep the workspaces

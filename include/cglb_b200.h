@@ -79,6 +79,18 @@ CGLB_API int cglb_kmv_sym(cglb_context* ctx, int kind, const double* xp, long n,
  * Pure query (no launch); benchmarks use it to name the kernel they time. */
 CGLB_API int cglb_kmv_sym_variant(const cglb_context* ctx, int d, long n, int nparts);
 
+/* ---- K1 in fp32-pair mode (the reference's fp32 switch, cglb/backend/pytorch/interface.py:96-110) ----------
+ * Same product as cglb_kmv_sym with the n^2 kernel-pair evaluations in FP32 (FP32 FMA pipe + MUFU rsqrt/ex2);
+ * v, y and all accumulation across tiles stay FP64.  Per-entry error ~1e-6 (expanded-form distances in
+ * fp32), d <= 32.  xpf comes from cglb_pack_inputs_f32: width cglb_packed_width_f32(d) floats,
+ * cglb_padded_rows(n) rows.
+ * replaces: the same call sites as cglb_kmv_sym when the model was created under set_default_float("fp32"). */
+CGLB_API int cglb_packed_width_f32(int d);
+CGLB_API int cglb_pack_inputs_f32(cglb_context* ctx, int kind, const double* x, long n, int d, const double* lengthscale,
+                         const double* shift, float* xpf, void* stream);
+CGLB_API int cglb_kmv_sym_f32(cglb_context* ctx, int kind, const float* xpf, long n, int d, const double* v, double* y,
+                     double variance, double diag, int part, int nparts, void* stream);
+
 /* y[0:nrows] = variance * K(rows, cols) v[0:ncols]   (rectangular, e.g. K_sf v of PredictCG)
  * replaces: `ksf @ new_v` at cglb/backend/pytorch/models.py:334 */
 CGLB_API int cglb_kmv_rect(cglb_context* ctx, int kind, const double* xp_rows, long nrows, const double* xp_cols,

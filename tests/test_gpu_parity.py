@@ -122,6 +122,46 @@ def test_dmma_sweep_duplicates_and_midsize(eng, monkeypatch):
     assert float((parts - y0).norm() / y0.norm()) <= 1e-12
 
 
+# ---- K1 in fp32-pair mode (f32sweep_impl.cuh): the fp32 switch of the reference ------------------------------------
+F32_TOL = 5e-6      # kernel pairs in FP32 (expanded-form distances, MUFU rsqrt/ex2); accumulation in FP64
+
+
+@pytest.mark.parametrize("kind,n,d", [("matern32", 1, 1), ("matern32", 2, 3), ("matern32", 300, 1), ("rbf", 777, 8),
+                                      ("matern32", 2500, 11), ("rbf", 2049, 3), ("matern32", 1025, 5), ("rbf", 900, 16),
+                                      ("matern32", 640, 20), ("rbf", 513, 32), ("matern32", 4100, 13)])
+def test_kmv_sym_f32_matches_oracle(eng, kind, n, d):
+    x, v, u, ls = _problem(n, d, seed=n + d)
+    dev = eng.device
+    xpf = eng.pack_f32(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    assert xpf.dtype == torch.float32 and xpf.shape[1] == (d + 4) // 4 * 4
+    K = o.kernel_dense(kind, x, x, ls, torch.tensor(1.3, dtype=f64))
+    ref = K @ v + 0.07 * v
+    y = eng.kmv_sym_f32(kind, xpf, n, d, v.to(dev), 1.3, 0.07)
+    assert y.dtype == f64
+    assert float((y.cpu() - ref).norm() / ref.norm()) <= F32_TOL
+    parts = sum(eng.kmv_sym_f32(kind, xpf, n, d, v.to(dev), 1.3, 0.07, part=p, nparts=3) for p in range(3))
+    assert float((parts.cpu() - ref).norm() / ref.norm()) <= F32_TOL
+
+
+def test_kmv_sym_f32_midsize_and_errors(eng):
+    dev = eng.device
+    n, d = 150001, 11
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(n, d, generator=g, dtype=f64, device=dev)
+    v = torch.randn(n, generator=g, dtype=f64, device=dev)
+    ls = torch.full((d,), 1.5, dtype=f64, device=dev)
+    xp, xpf = eng.pack("matern32", x, ls, x.mean(0)), eng.pack_f32("matern32", x, ls, x.mean(0))
+    y64 = eng.kmv_sym("matern32", xp, n, d, v, 1.0, 0.01)
+    y32 = eng.kmv_sym_f32("matern32", xpf, n, d, v, 1.0, 0.01)
+    assert float((y32 - y64).norm() / y64.norm()) <= F32_TOL
+    parts = sum(eng.kmv_sym_f32("matern32", xpf, n, d, v, 1.0, 0.01, part=p, nparts=8) for p in range(8))
+    assert float((parts - y64).norm() / y64.norm()) <= F32_TOL
+    with pytest.raises(cb.CglbError):       # fp64 packed array handed to the fp32 entry
+        eng.kmv_sym_f32("matern32", xp, n, d, v, 1.0, 0.01)
+    with pytest.raises(cb.CglbError):       # d > 32 has no fp32-pair sweep: fails loudly
+        eng.kmv_sym_f32("matern32", torch.zeros(128, 44, dtype=torch.float32, device=dev), 100, 40, v[:100].contiguous(), 1.0, 0.0)
+
+
 @pytest.mark.parametrize("kind,d,lsval", [("matern32", 3, 0.05), ("rbf", 3, 0.05), ("matern32", 8, 30.0)])
 def test_kmv_extreme_lengthscales(eng, kind, d, lsval):
     """expanded-form distances must survive tiny lengthscales (huge |a|^2) and huge ones (K ~ all ones)."""
