@@ -195,22 +195,24 @@ def run_b200(args, rank, world, local_rank):
         n = args.n
     th = THETAS[args.theta]
     x_h, y_h, z_h = synthetic(n, d, M)
+    fdt = torch.float32 if args.float_type == "fp32" else torch.float64      # exploration only: BASELINE.json's metric is fp64
+    x_h, y_h, z_h = x_h.to(fdt), y_h.to(fdt), z_h.to(fdt)
     x_pin, y_pin = x_h.pin_memory(), y_h.pin_memory()
 
     # model exactly as interface.py:263-323 builds it (Z = M random rows: stand-in for ConditionalVariance,
     # which runs on the host outside the timed step)
-    lik = cb.GaussianLikelihood(noise_constraint=cb.GreaterThan(1e-6)).double()
+    lik = cb.GaussianLikelihood(noise_constraint=cb.GreaterThan(1e-6)).to(fdt)
     lik.noise = th["noise"]
-    base = (cb.MaternKernel(nu=1.5, ard_num_dims=d) if kind == "matern32" else cb.RBFKernel(ard_num_dims=d)).double()
-    base.lengthscale = torch.full((d,), th["ls"](d), dtype=torch.float64)
-    scale = cb.ScaleKernel(base).double()
+    base = (cb.MaternKernel(nu=1.5, ard_num_dims=d) if kind == "matern32" else cb.RBFKernel(ard_num_dims=d)).to(fdt)
+    base.lengthscale = torch.full((d,), th["ls"](d), dtype=fdt)
+    scale = cb.ScaleKernel(base).to(fdt)
     scale.outputscale = th["variance"]
     ipk = cb.InducingPointKernel(scale, z_h, likelihood=lik)
-    x_dev = torch.empty(n, d, dtype=torch.float64, device=dev)
-    y_dev = torch.empty(n, dtype=torch.float64, device=dev)
+    x_dev = torch.empty(n, d, dtype=fdt, device=dev)
+    y_dev = torch.empty(n, dtype=fdt, device=dev)
     x_dev.copy_(x_pin, non_blocking=True)
     y_dev.copy_(y_pin, non_blocking=True)
-    model = cb.CGLB((x_dev, y_dev), lik, ipk).double().to(dev)
+    model = cb.CGLB((x_dev, y_dev), lik, ipk).to(fdt).to(dev)
     data = (x_dev, y_dev)
     lower_bound = cb.LowerBoundCG(model, shard=shard)
     params = list(model.parameters())
@@ -228,7 +230,7 @@ def run_b200(args, rank, world, local_rank):
         xv[ls_slice] = lsv + np.log(-np.expm1(-lsv))            # inverse softplus
         return xv
 
-    h2d_bytes = x_pin.numel() * 8 + y_pin.numel() * 8 + x0.size * 8
+    h2d_bytes = x_pin.numel() * x_pin.element_size() + y_pin.numel() * y_pin.element_size() + x0.size * 8
     d2h_bytes = (x0.size + 1) * 8
     stats = []
 
@@ -311,9 +313,11 @@ def run_b200(args, rank, world, local_rank):
     line = {
         "metric": "cglb_bound_grad_step_time", "value": ms_step * 1e-3, "unit": "s/step", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc if not args.n else f"{desc} (n overridden to {n})", "theta": args.theta,
-                   "kernel": kind, "n": n, "d": d, "M": M, "parallelism": f"row-sharded x{world}",
+        "vs_baseline": None, "dtype": "f64" if args.float_type == "fp64" else "f32 kernel pairs, f64 accumulation and linear algebra",
+        "data": "synthetic",
+        "config": {"workload": (desc if not args.n else f"{desc} (n overridden to {n})") +
+                               ("" if args.float_type == "fp64" else " -- run in the fp32 mode of the API, NOT the fp64 metric of BASELINE.json"),
+                   "theta": args.theta, "kernel": kind, "n": n, "d": d, "M": M, "parallelism": f"row-sharded x{world}",
                    "cg": "reference defaults (max_error=1, max_cg_iter=100, restart=40), warm start carried across steps, "
                          "lengthscales perturbed by (1, 1.01, 0.99) per step",
                    "cg_steps": [s["cg"] for s in stats], "kv_sweeps_per_step": [s["matvecs"] for s in stats],
@@ -345,6 +349,12 @@ def run_b200(args, rank, world, local_rank):
                                "ms_per_launch": float(kt[1]) / max(ksum.get("kmv_bwd_sym", (1, 0))[0], 1)},
             "dense_trsm_syrk_gemm": {"share_of_step": float(kt[3]) / float(t_dev[0]) if float(t_dev[0]) else None}},
     }
+    if args.float_type == "fp32" and d <= 32:
+        # exploration: the sweep that ran is f32_sweep_kernel (FP32 FMA + MUFU pipes); the FP64 roofline does not apply
+        line["roofline"].update({"kernel": "K1 symmetric matrix-free K*v: f32_sweep_kernel (FP32 kernel pairs, FP64 accumulation)",
+                                 "frac": None, "achieved_evaluated": None, "frac_evaluated": None, "fp64_pipe_utilisation_ncu": None,
+                                 "note": "fp32 mode of the API: 2 MUFU + ~17 FP32 + ~3 other instructions per pair, issue-bound; "
+                                         "`achieved` is still the nominal (3d+7) n^2 figure, not comparable with the FP64 peak"})
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(kind, n, d, M, th, stats)
     print(json.dumps(line), flush=True)
@@ -392,6 +402,8 @@ def main():
     ap.add_argument("--theta", default="init", choices=sorted(THETAS))
     ap.add_argument("--n", type=int, default=0, help="override n (exploration only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--float-type", default="fp64", choices=["fp64", "fp32"],
+                    help="fp32: the API's fp32 switch (FP32 kernel pairs); exploration only, the headline metric is fp64")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

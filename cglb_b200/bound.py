@@ -225,8 +225,12 @@ class BoundEvaluator:
         # ---- sharded parts: [sweep(d+1) | ls(d) | var(1) | Z(m*d)] in one buffer, one all-reduce
         acc = eng.zeros(2 * d + 2 + m * d)
         sweep, o_ls, o_var, o_z = acc[:d + 1], acc[d + 1:2 * d + 1], acc[2 * d + 1:2 * d + 2], acc[2 * d + 2:]
-        eng.kmv_bwd_sym(kind, self.xp, n, d, u, vf.contiguous(), variance, lengthscale, sweep,
-                        part=shard.rank, nparts=shard.world)                            # K2
+        if self.pair_dtype == "f32":
+            eng.kmv_bwd_sym_f32(kind, self.xpf, self.xp, n, d, u, vf.contiguous(), variance, lengthscale, sweep,
+                                part=shard.rank, nparts=shard.world)                    # K2, FP32 kernel pairs
+        else:
+            eng.kmv_bwd_sym(kind, self.xp, n, d, u, vf.contiguous(), variance, lengthscale, sweep,
+                            part=shard.rank, nparts=shard.world)                        # K2
         Linv = eng.tri_inverse(terms.L)
         LinvT = Linv.t().contiguous()
         LBinvT = terms.LBinv.t().contiguous()

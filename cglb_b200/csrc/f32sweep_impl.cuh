@@ -217,6 +217,253 @@ __global__ void __launch_bounds__(WARPS * 32, 1) f32_sweep_kernel(const SweepArg
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2 in fp32-pair mode: the fused backward sweep of kmv_bwd_kernel (kmv_impl.cuh) with the pair
+// arithmetic in FP32.  Thread-private FP32 partials live for one 64-column tile only and are flushed into FP64
+// accumulators (row sums R, the d cross terms -2 X_q, the variance sum) at every tile.
+// ---------------------------------------------------------------------------------------------
+struct BwdArgsF32 {
+    const float* xp;                       // packed fp32 [n_pad][DPF]
+    const float* wcol; const float* ucol;  // padded float copies of w and u
+    double* rsum;                          // R (atomics)
+    double* gout;                          // [D+1]: -2 X_q ..., variance sum
+    long n, nb, nitems;
+    int part, nparts;
+};
+
+template <int KIND>
+__device__ __forceinline__ void kappa_dweight_f32(float q, float& kap, float& ew) {
+    if (KIND == CGLB_MATERN32) {
+        q = fmaxf(q, 1e-30f);
+        float y;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(q));
+        const float s = q * y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ew) : "f"(s * -1.4426950408889634f));
+        kap = fmaf(s, ew, ew);
+    } else {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ew) : "f"(fmaxf(q, 0.0f) * -1.4426950408889634f));
+        kap = ew;
+    }
+}
+
+template <int KIND, int D, int TI, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) f32_bwd_kernel(const BwdArgsF32 args) {
+    constexpr int DPF = (D + 4) & ~3;
+    constexpr int kThreads = WARPS * 32;
+    constexpr int BI = kThreads * TI;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_x = reinterpret_cast<float*>(smem_raw);                    // [kStages][kBJ*DPF]
+    float* s_v = s_x + kStages * kBJ * DPF;                             // [kStages][2][kBJ]  (w, u)
+    float* s_col = s_v + kStages * 2 * kBJ;                             // [2][WARPS][kBJ]
+    double* s_red = reinterpret_cast<double*>(s_col + 2 * WARPS * kBJ); // [WARPS][D+2]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_red + WARPS * (D + 2));
+    uint64_t* s_empty = s_full + kStages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    struct Cur {
+        long tau, I, C, c0; int tile, ntiles; bool valid;
+    };
+    auto load_item = [&](Cur& c) {
+        const long t = c.tau * args.nparts + args.part;
+        c.valid = t < args.nitems;
+        if (!c.valid) return;
+        item_to_blocks_sym(t, c.I, c.C);
+        c.c0 = c.C * BI;
+        long cend = c.c0 + BI;
+        if (cend > args.n) cend = args.n;
+        c.ntiles = (int)((cend - c.c0 + kBJ - 1) / kBJ);
+        c.tile = 0;
+    };
+    int pstage = 0, stage = 0;
+    uint32_t pphase = 0, phase = 0;
+    auto produce = [&](Cur& pc) {
+        if (!pc.valid) return;
+        mbar_wait(&s_empty[pstage], pphase ^ 1);
+        const long j0 = pc.c0 + (long)pc.tile * kBJ;
+        mbar_expect_tx(&s_full[pstage], (uint32_t)((kBJ * DPF + 2 * kBJ) * sizeof(float)));
+        tma_load_1d(s_x + pstage * kBJ * DPF, args.xp + j0 * DPF, kBJ * DPF * sizeof(float), &s_full[pstage]);
+        tma_load_1d(s_v + pstage * 2 * kBJ, args.wcol + j0, kBJ * sizeof(float), &s_full[pstage]);
+        tma_load_1d(s_v + pstage * 2 * kBJ + kBJ, args.ucol + j0, kBJ * sizeof(float), &s_full[pstage]);
+        if (++pstage == kStages) { pstage = 0; pphase ^= 1; }
+        if (++pc.tile == pc.ntiles) { pc.tau += gridDim.x; load_item(pc); }
+    };
+
+    Cur cc;
+    cc.tau = blockIdx.x;
+    load_item(cc);
+    Cur pc = cc;
+    if (tid == 0) {
+#pragma unroll 1
+        for (int i = 0; i < kPrefetch; ++i) produce(pc);
+    }
+    int colbuf = 0;
+    double gq[D], gvar = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) gq[k] = 0.0;
+
+    while (cc.valid) {
+        const bool offdiag = cc.I != cc.C;
+        const float half = offdiag ? 1.0f : 0.5f;
+        const long r0 = cc.I * BI;
+        float a2[TI][D], na[TI], ui[TI], wi[TI];
+        double racc[TI];
+        bool live[TI];
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti) {
+            const long row = r0 + ti * kThreads + tid;
+            live[ti] = row < args.n;
+            const float4* src = reinterpret_cast<const float4*>(args.xp + (live[ti] ? row : 0) * DPF);
+            float tmp[DPF];
+#pragma unroll
+            for (int h = 0; h < DPF / 4; ++h) {
+                const float4 p = __ldg(src + h);
+                tmp[4 * h] = p.x; tmp[4 * h + 1] = p.y; tmp[4 * h + 2] = p.z; tmp[4 * h + 3] = p.w;
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) a2[ti][k] = live[ti] ? -2.0f * tmp[k] : 0.0f;
+            na[ti] = live[ti] ? tmp[DPF - 1] : 0.0f;
+            ui[ti] = live[ti] ? half * __ldg(args.ucol + row) : 0.0f;
+            wi[ti] = live[ti] ? half * __ldg(args.wcol + row) : 0.0f;
+            racc[ti] = 0.0;
+        }
+        const int ntiles = cc.ntiles;
+        const long c0 = cc.c0;
+#pragma unroll 1
+        for (int tile = 0; tile < ntiles; ++tile) {
+            if (tid == 0) produce(pc);
+            __syncwarp();
+            mbar_wait(&s_full[stage], phase);
+            const float* sx = s_x + stage * kBJ * DPF;
+            const float* sw = s_v + stage * 2 * kBJ;
+            const float* su = sw + kBJ;
+            float* scol = s_col + (colbuf * WARPS + warp) * kBJ;
+            float rt[TI], gqt[D], gvt = 0.0f;
+#pragma unroll
+            for (int ti = 0; ti < TI; ++ti) rt[ti] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) gqt[k] = 0.0f;
+#pragma unroll 1
+            for (int jg = 0; jg < kBJ; jg += kCG) {
+                float c[kCG];
+#pragma unroll
+                for (int jj = 0; jj < kCG; ++jj) {
+                    const float4* bp = reinterpret_cast<const float4*>(sx + (jg + jj) * DPF);
+                    float b[DPF];
+#pragma unroll
+                    for (int h = 0; h < DPF / 4; ++h) {
+                        const float4 p = bp[h];
+                        b[4 * h] = p.x; b[4 * h + 1] = p.y; b[4 * h + 2] = p.z; b[4 * h + 3] = p.w;
+                    }
+                    const float wj = sw[jg + jj], uj = su[jg + jj];
+                    float cs = 0.0f, wq[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) wq[k] = 0.0f;
+#pragma unroll
+                    for (int ti = 0; ti < TI; ++ti) {
+                        float q = na[ti] + b[DPF - 1];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) q = fmaf(a2[ti][k], b[k], q);
+                        float kap, ew;
+                        kappa_dweight_f32<KIND>(q, kap, ew);
+                        const float om = fmaf(wi[ti], uj, ui[ti] * wj);
+                        const float cw = ew * om;
+                        gvt = fmaf(kap, om, gvt);
+                        rt[ti] += cw;
+                        cs += cw;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) wq[k] = fmaf(cw, a2[ti][k], wq[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < D; ++k) gqt[k] = fmaf(b[k], wq[k], gqt[k]);
+                    c[jj] = cs;
+                }
+                if (offdiag) {
+                    col_reduce_f32<kCG>(c, lane);
+                    if ((lane & (32 / kCG - 1)) == 0) scol[jg + reduced_col<kCG>(lane)] = c[0];
+                }
+            }
+            // FP32 partials of this tile -> FP64 accumulators
+#pragma unroll
+            for (int ti = 0; ti < TI; ++ti) racc[ti] += (double)rt[ti];
+#pragma unroll
+            for (int k = 0; k < D; ++k) gq[k] += (double)gqt[k];
+            gvar += (double)gvt;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+
+            if (offdiag) {
+                __syncthreads();
+                if (tid < kBJ) {
+                    const long j = c0 + (long)tile * kBJ + tid;
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < WARPS; ++w) s += (double)s_col[(colbuf * WARPS + w) * kBJ + tid];
+                    if (j < args.n) atomicAdd(args.rsum + j, s);
+                }
+                colbuf ^= 1;
+            }
+        }
+        const double rscale = offdiag ? 1.0 : 2.0;
+#pragma unroll
+        for (int ti = 0; ti < TI; ++ti)
+            if (live[ti]) atomicAdd(args.rsum + r0 + ti * kThreads + tid, rscale * racc[ti]);
+        cc.tau += gridDim.x;
+        load_item(cc);
+    }
+
+    // block reduction of the thread-private accumulators -> one atomic per CTA per component
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const double s = warp_sum(gq[k]);
+        if (lane == 0) s_red[warp * (D + 2) + k] = s;
+    }
+    {
+        const double s = warp_sum(gvar);
+        if (lane == 0) s_red[warp * (D + 2) + D] = s;
+    }
+    __syncthreads();
+    if (tid <= D) {
+        double s = 0.0;
+        for (int w = 0; w < WARPS; ++w) s += s_red[w * (D + 2) + tid];
+        atomicAdd(args.gout + tid, s);
+    }
+}
+
+template <int KIND, int D, int TI, int WARPS>
+static int launch_f32_bwd(Context* ctx, BwdArgsF32 a, cudaStream_t st) {
+    constexpr int DPF = (D + 4) & ~3;
+    constexpr long BI = WARPS * 32 * TI;
+    a.nb = (a.n + BI - 1) / BI;
+    a.nitems = a.nb * (a.nb + 1) / 2;
+    auto kern = f32_bwd_kernel<KIND, D, TI, WARPS>;
+    const size_t smem = (size_t)(kStages * kBJ * DPF + kStages * 2 * kBJ + 2 * WARPS * kBJ) * sizeof(float) +
+                        (size_t)WARPS * (D + 2) * sizeof(double) + 2 * kStages * sizeof(uint64_t);
+    CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
+    if (my_items <= 0) return CGLB_OK;
+    const int grid = (int)(my_items < ctx->num_sms ? my_items : ctx->num_sms);
+    kern<<<grid, WARPS * 32, smem, st>>>(a);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+template <int KIND, int D>
+static int run_f32_bwd(Context* ctx, const BwdArgsF32& a, cudaStream_t st) {
+    if constexpr (D <= 16) {
+        if (count_items(a.n, a.n, true, a.nparts, 8 * 32 * 4) >= 12L * ctx->num_sms) return launch_f32_bwd<KIND, D, 4, 8>(ctx, a, st);
+    }
+    if (count_items(a.n, a.n, true, a.nparts, 8 * 32 * 2) >= 12L * ctx->num_sms) return launch_f32_bwd<KIND, D, 2, 8>(ctx, a, st);
+    return launch_f32_bwd<KIND, D, 1, 8>(ctx, a, st);
+}
+
 template <int KIND, int D, int TI, int WARPS>
 static int launch_f32(Context* ctx, SweepArgsF32 a, cudaStream_t st) {
     constexpr int DPF = (D + 4) & ~3;
@@ -262,6 +509,8 @@ static int run_f32(Context* ctx, const SweepArgsF32& a, cudaStream_t st) {
 }
 
 typedef int (*f32_fn)(Context*, int kind, const SweepArgsF32&, cudaStream_t);
+typedef int (*f32_bwd_fn)(Context*, int kind, const BwdArgsF32&, cudaStream_t);
 f32_fn get_f32_fn(int d);
+f32_bwd_fn get_f32_bwd_fn(int d);
 
 }  // namespace cglb

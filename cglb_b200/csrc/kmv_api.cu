@@ -57,6 +57,16 @@ __global__ void kmv_prologue_f32_kernel(const double* __restrict__ v, long n, lo
     if (i < n) y[i] = diag * v[i];
 }
 
+__global__ void bwd_prologue_f32_kernel(const double* __restrict__ u, const double* __restrict__ w, long n, long n_pad,
+                                        float* __restrict__ upad, float* __restrict__ wpad, double* __restrict__ rsum) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) {
+        upad[i] = (i < n) ? (float)u[i] : 0.0f;
+        wpad[i] = (i < n) ? (float)w[i] : 0.0f;
+        rsum[i] = 0.0;
+    }
+}
+
 // vpad = [v, 0...]; y = diag * v (or 0)
 __global__ void kmv_prologue_kernel(const double* __restrict__ v, long n, long n_pad, double* __restrict__ vpad,
                                     double* __restrict__ y, long ny, double diag) {
@@ -110,6 +120,7 @@ __global__ void bwd_epilogue_kernel(const double* __restrict__ xp, long n, int d
 #define X(DD)                                                              \
     int sweep_d##DD(Context*, int, int, const SweepArgs&, cudaStream_t);   \
     int f32_d##DD(Context*, int, const SweepArgsF32&, cudaStream_t);       \
+    int f32_bwd_d##DD(Context*, int, const BwdArgsF32&, cudaStream_t);     \
     int knm_d##DD(Context*, int, int, const KnmArgs&, cudaStream_t);
 CGLB_KMV_DIMS_LIST
 #undef X
@@ -131,6 +142,18 @@ f32_fn get_f32_fn(int d) {
 #define X(DD) \
     case DD:  \
         return f32_d##DD;
+        CGLB_KMV_DIMS_LIST
+#undef X
+        default:
+            return nullptr;
+    }
+}
+
+f32_bwd_fn get_f32_bwd_fn(int d) {
+    switch (d) {
+#define X(DD) \
+    case DD:  \
+        return f32_bwd_d##DD;
         CGLB_KMV_DIMS_LIST
 #undef X
         default:
@@ -250,6 +273,44 @@ extern "C" int cglb_kmv_sym_f32(cglb_context* c, int kind, const float* xpf, lon
     SweepArgsF32 a{};
     a.xp = xpf; a.vcol = vpad32; a.y = y; a.n = n; a.variance = variance; a.part = part; a.nparts = nparts;
     return f(ctx, kind, a, st);
+}
+
+extern "C" int cglb_kmv_bwd_sym_f32(cglb_context* c, int kind, const float* xpf, const double* xp, long n, int d, const double* u,
+                                    const double* w, double variance, const double* lengthscale, double* out, int part,
+                                    int nparts, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx != nullptr, "null context");
+    CGLB_CHECK_ARG(nparts >= 1 && part >= 0 && part < nparts, "part/nparts");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    if (n == 0) return CGLB_OK;
+    CGLB_CHECK_ARG(xpf && xp && u && w && out && lengthscale, "null pointer");
+    f32_bwd_fn f = d <= CGLB_MAX_REGISTER_D ? get_f32_bwd_fn(d) : nullptr;
+    if (!f) {
+        set_error("fp32-pair backward sweep: d=%d is not instantiated (d <= %d only; use cglb_kmv_bwd_sym)", d, CGLB_MAX_REGISTER_D);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long v_pad = (n + 1023) / 1024 * 1024;
+    int rc = ensure_vpad(ctx, v_pad);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, kScratchScalars);
+    if (rc) return rc;
+    // float copies of u and w live in the (double) u / v workspaces
+    float* upad32 = reinterpret_cast<float*>(ctx->upad);
+    float* wpad32 = reinterpret_cast<float*>(ctx->vpad);
+    bwd_prologue_f32_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(u, w, n, v_pad, upad32, wpad32, ctx->rsum);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    CGLB_CUDA_OK(cudaMemsetAsync(ctx->scratch, 0, sizeof(double) * kScratchScalars, st));
+    BwdArgsF32 a{};
+    a.xp = xpf; a.wcol = wpad32; a.ucol = upad32; a.rsum = ctx->rsum; a.gout = ctx->scratch; a.n = n; a.part = part; a.nparts = nparts;
+    rc = f(ctx, kind, a, st);
+    if (rc) return rc;
+    const double cfac = (kind == CGLB_MATERN32) ? 1.0 : 2.0;
+    bwd_epilogue_kernel<<<d, 256, 0, st>>>(xp, n, d, packed_width(d), ctx->rsum, ctx->scratch, lengthscale, variance, cfac, out, 1);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
 }
 
 extern "C" int cglb_kmv_sym_variant(const cglb_context* c, int d, long n, int nparts) {

@@ -41,6 +41,11 @@ int CGLB_CAT(f32_d, CGLB_KMV_D)(Context* ctx, int kind, const SweepArgsF32& a, c
     return kind == CGLB_MATERN32 ? run_f32<CGLB_MATERN32, D>(ctx, a, st) : run_f32<CGLB_RBF, D>(ctx, a, st);
 }
 
+int CGLB_CAT(f32_bwd_d, CGLB_KMV_D)(Context* ctx, int kind, const BwdArgsF32& a, cudaStream_t st) {
+    constexpr int D = CGLB_KMV_D;
+    return kind == CGLB_MATERN32 ? run_f32_bwd<CGLB_MATERN32, D>(ctx, a, st) : run_f32_bwd<CGLB_RBF, D>(ctx, a, st);
+}
+
 int CGLB_CAT(knm_d, CGLB_KMV_D)(Context* ctx, int kind, int bwd, const KnmArgs& a, cudaStream_t st) {
     constexpr int D = CGLB_KMV_D;
     if (kind == CGLB_MATERN32) return run_knm<CGLB_MATERN32, D>(ctx, bwd, a, st);

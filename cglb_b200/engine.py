@@ -149,6 +149,13 @@ class Engine:
             self.stream()), "cglb_kmv_sym_f32"))
         return out
 
+    def kmv_bwd_sym_f32(self, kind, xpf, xp, n, d, u, w, variance, lengthscale, out, part=0, nparts=1) -> Tensor:
+        _req(xpf, "xpf", torch.float32); _req(xp, "xp"); _req(u, "u"); _req(w, "w"); _req(lengthscale, "lengthscale"); _req(out, "out")
+        self._timed("kmv_bwd_sym", lambda: check(self.lib.cglb_kmv_bwd_sym_f32(
+            self.ctx, KIND_IDS[kind], ptr(xpf), ptr(xp), n, d, ptr(u), ptr(w), float(variance), ptr(lengthscale), ptr(out),
+            int(part), int(nparts), self.stream()), "cglb_kmv_bwd_sym_f32"))
+        return out
+
     def kmv_rect(self, kind, xp_rows, nrows, xp_cols, ncols, d, v, variance, out=None) -> Tensor:
         _req(xp_rows, "xp_rows"); _req(xp_cols, "xp_cols"); _req(v, "v")
         if out is None:

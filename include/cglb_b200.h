@@ -90,6 +90,11 @@ CGLB_API int cglb_pack_inputs_f32(cglb_context* ctx, int kind, const double* x, 
                          const double* shift, float* xpf, void* stream);
 CGLB_API int cglb_kmv_sym_f32(cglb_context* ctx, int kind, const float* xpf, long n, int d, const double* v, double* y,
                      double variance, double diag, int part, int nparts, void* stream);
+/* K2 in fp32-pair mode: same contract as cglb_kmv_bwd_sym; the sweep reads xpf, the O(n d) epilogue reads the
+ * fp64 packed array xp of the same inputs. */
+CGLB_API int cglb_kmv_bwd_sym_f32(cglb_context* ctx, int kind, const float* xpf, const double* xp, long n, int d,
+                         const double* u, const double* w, double variance, const double* lengthscale, double* out,
+                         int part, int nparts, void* stream);
 
 /* y[0:nrows] = variance * K(rows, cols) v[0:ncols]   (rectangular, e.g. K_sf v of PredictCG)
  * replaces: `ksf @ new_v` at cglb/backend/pytorch/models.py:334 */

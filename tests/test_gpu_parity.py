@@ -143,6 +143,30 @@ def test_kmv_sym_f32_matches_oracle(eng, kind, n, d):
     assert float((parts.cpu() - ref).norm() / ref.norm()) <= F32_TOL
 
 
+@pytest.mark.parametrize("kind,n,d", [("matern32", 300, 1), ("rbf", 777, 8), ("matern32", 2500, 11), ("rbf", 2049, 3),
+                                      ("matern32", 640, 20), ("rbf", 513, 32), ("matern32", 4100, 5)])
+def test_kmv_bwd_f32_matches_autograd_of_oracle(eng, kind, n, d):
+    """fp32-pair backward sweep: d(u^T K w)/d{lengthscale, variance} against autograd through the fp64 oracle.
+    Tolerance 2e-4 of the gradient norm (FP32 kernel pairs and FP32 per-tile partial sums)."""
+    x, v, u, ls = _problem(n, d, seed=n + 3 * d)
+    dev = eng.device
+    xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    xpf = eng.pack_f32(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    out = eng.zeros(d + 1)
+    eng.kmv_bwd_sym_f32(kind, xpf, xp, n, d, u.to(dev), v.to(dev), 1.3, ls.to(dev), out)
+    lsr = ls.clone().requires_grad_(True)
+    varr = torch.tensor(1.3, dtype=f64, requires_grad=True)
+    f = u @ (o.kernel_dense(kind, x, x, lsr, varr) @ v)
+    gl, gv = torch.autograd.grad(f, [lsr, varr])
+    ref = torch.cat([gl.reshape(-1), gv.reshape(1)])
+    assert float((out.cpu() - ref).norm() / ref.norm()) <= 2e-4
+    # partition of the work items sums to the full gradient
+    parts = eng.zeros(d + 1)
+    for p in range(3):
+        eng.kmv_bwd_sym_f32(kind, xpf, xp, n, d, u.to(dev), v.to(dev), 1.3, ls.to(dev), parts, part=p, nparts=3)
+    assert float((parts.cpu() - ref).norm() / ref.norm()) <= 2e-4
+
+
 def test_kmv_sym_f32_midsize_and_errors(eng):
     dev = eng.device
     n, d = 150001, 11
