@@ -400,7 +400,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--theta", default="init", choices=sorted(THETAS))
-    ap.add_argument("--n", type=int, default=0, help="override n (exploration only; the line says so)")
+    ap.add_argument("--n", "--n-rows", dest="n", type=int, default=0,
+                    help="override n (exploration only; the line says so); spell it --n-rows under torch.distributed.run, whose "
+                         "own parser claims the abbreviation --n")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--float-type", default="fp64", choices=["fp64", "fp32"],
                     help="fp32: the API's fp32 switch (FP32 kernel pairs); exploration only, the headline metric is fp64")
