@@ -17,4 +17,17 @@ bool dsweep_supported(const Context* ctx, int d, long n, int nparts) {
     return items >= 8L * ctx->num_sms;
 }
 
+// same question for the backward sweep (dmma_bwd_kernel)
+bool dbwd_supported(const Context* ctx, int d, long n, int nparts) {
+    if (d > CGLB_MAX_REGISTER_D) return false;
+    if (nparts <= 0) return d >= 2;
+    // measured on B200 (tools/dev_time_sweeps.py, Gpairs/s DMMA vs register): d = 3 833 vs 854, 4 855 vs 931, 5 741 vs 730,
+    // 6 863 vs 779, 7 742 vs 645, 8 772 vs 697, 9 564 vs 573 (9 coordinates in two 8-slot tiles), 10 562 vs 557,
+    // 11 568 vs 515, 13 525 vs 388, 16 558 vs 359, 19 407 vs 294, 24 365 vs 233, 32 318 vs 170
+    if (d < 6 || d == 9) return false;
+    const long n_chunks = (n + 1023) / 1024;
+    const long items = 4 * n_chunks * (n_chunks + 1) / 2 / nparts;
+    return items >= 8L * ctx->num_sms;
+}
+
 }  // namespace cglb

@@ -272,4 +272,254 @@ static int run_dsweep(Context* ctx, SweepArgs a, cudaStream_t st) {
     return CGLB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K2 (fused backward sweep) on DMMA for 10 <= d <= 32.  Same tiling as dmma_sweep_kernel; per
+// n-tile (8 columns x the warp's 32 rows):
+//   S = A_I A_J^T on DMMA -> (kappa, e') on the fragments; omega = u_i w_j + w_i u_j; c = e' omega
+//   gvar += kappa omega;  row sums of c in registers, column sums through the transposing butterfly + one RED
+//   cross term: Y_I += C A_J as a SECOND DMMA product.  The contraction index (the 8 columns) can be permuted
+//   freely, so the thread's own two c values (columns 2 t4, 2 t4 + 1 of the C fragment) serve directly as the
+//   A fragment of two k-steps whose B fragments are rows 2 t4 / 2 t4 + 1 of the column tile: no shuffles, no
+//   shared-memory staging of C.  X_q = sum_i a_iq Y_iq is formed once per item.
+// Tiles overlapping the row block visit ordered pairs with halved weights and doubled row sums, as in the
+// register-resident kernel.
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int D, int WARPS, int MT>
+__global__ void __launch_bounds__(WARPS * 32, 1) dmma_bwd_kernel(const SweepArgs args, const long n_chunks) {
+    constexpr int DP = SmemLayout<D>::DP;
+    constexpr int KS = (DP + 3) / 4;
+    constexpr int NQ = (D + 7) / 8;     // 8-slot coordinate tiles of Y (slots >= D are ignored)
+    constexpr int DS_THREADS = WARPS * 32, DS_ROWS = WARPS * 8 * MT;
+    constexpr int WROWS = 8 * MT;
+    using Cur = DCursor<DS_ROWS>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_tab[kExpTabBig];
+    __shared__ double s_red[WARPS][4 * NQ + 1];
+    double* s_x = reinterpret_cast<double*>(smem_raw);                    // [DS_STAGES][kBJ*DP]
+    double* s_wu = s_x + DS_STAGES * kBJ * DP;                            // [DS_STAGES][2][kBJ]  (w, u)
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_wu + DS_STAGES * 2 * kBJ);
+    uint64_t* s_empty = s_full + DS_STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int i = tid; i < kExpTabBig; i += DS_THREADS) s_tab[i] = args.exp_tab[kExpTabSmall + i];
+    // fragment loads may run past a packed row (into the next row, the next stage or the w/u slices): all finite
+    for (int i = tid; i < DS_STAGES * kBJ * DP + DS_STAGES * 2 * kBJ; i += DS_THREADS) s_x[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < DS_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+    int pstage = 0, stage = 0;
+    uint32_t pphase = 0, phase = 0;
+    auto produce = [&](Cur& pc) {
+        if (!pc.valid) return;
+        mbar_wait(&s_empty[pstage], pphase ^ 1);
+        const long j0 = pc.c0 + (long)pc.tile * kBJ;
+        mbar_expect_tx(&s_full[pstage], (uint32_t)((kBJ * DP + 2 * kBJ) * sizeof(double)));
+        tma_load_1d(s_x + pstage * kBJ * DP, args.xp_cols + j0 * DP, kBJ * DP * sizeof(double), &s_full[pstage]);
+        tma_load_1d(s_wu + pstage * 2 * kBJ, args.vcol + j0, kBJ * sizeof(double), &s_full[pstage]);
+        tma_load_1d(s_wu + pstage * 2 * kBJ + kBJ, args.ucol + j0, kBJ * sizeof(double), &s_full[pstage]);
+        if (++pstage == DS_STAGES) { pstage = 0; pphase ^= 1; }
+        pc.next_tile(args, n_chunks);
+    };
+
+    Cur cc;
+    cc.start(args, n_chunks);
+    Cur pc = cc;
+    if (tid == 0) {
+#pragma unroll 1
+        for (int i = 0; i < DS_STAGES / 2; ++i) produce(pc);
+    }
+    double gql[NQ][2], gvar = 0.0;       // thread-private: -2 X_q for slots 8 nq + 2 t4 + e, variance sum
+#pragma unroll
+    for (int nq = 0; nq < NQ; ++nq) gql[nq][0] = gql[nq][1] = 0.0;
+
+    while (cc.valid) {
+        const long r0 = cc.r0;
+        const long c0 = cc.c0;
+        const int ntiles = cc.ntiles;
+        double af[MT][KS], na[MT], ui[MT], wi[MT], racc[MT], yq[MT][NQ][2];
+        bool live[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const long row = r0 + warp * WROWS + i * 8 + g;
+            live[i] = row < args.nrows;
+            const double* src = args.xp_rows + (live[i] ? row : 0) * DP;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int k = 4 * ks + t4;
+                const double val = (live[i] && k < DP) ? __ldg(src + k) : 0.0;
+                af[i][ks] = (k == DP - 1) ? 1.0 : -2.0 * val;
+            }
+            na[i] = live[i] ? __ldg(src + DP - 1) : 0.0;
+            ui[i] = live[i] ? __ldg(args.ucol + row) : 0.0;
+            wi[i] = live[i] ? __ldg(args.vcol + row) : 0.0;
+            racc[i] = 0.0;
+#pragma unroll
+            for (int nq = 0; nq < NQ; ++nq) yq[i][nq][0] = yq[i][nq][1] = 0.0;
+        }
+#pragma unroll 1
+        for (int tile = 0; tile < ntiles; ++tile) {
+            if (tid == 0) produce(pc);
+            __syncwarp();
+            mbar_wait(&s_full[stage], phase);
+            const double* sx = s_x + stage * kBJ * DP;
+            const double* sw = s_wu + stage * 2 * kBJ;
+            const double* su = sw + kBJ;
+            const long j0 = c0 + (long)tile * kBJ;
+            const bool offdiag = j0 >= r0 + DS_ROWS;
+            const double half = offdiag ? 1.0 : 0.5, rs = offdiag ? 1.0 : 2.0;
+            double hu[MT], hw[MT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) { hu[i] = half * ui[i]; hw[i] = half * wi[i]; }
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                double c8[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int col0 = hh * 32 + j * 8;
+                    double bf[KS];
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) bf[ks] = sx[(col0 + g) * DP + 4 * ks + t4];
+                    double acc[MT][2];
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        dmma884c(acc[i], af[i][0], bf[0], na[i], na[i]);
+#pragma unroll
+                        for (int ks = 1; ks < KS; ++ks) dmma884c(acc[i], af[i][ks], bf[ks], acc[i][0], acc[i][1]);
+                    }
+                    const double2 w2 = *reinterpret_cast<const double2*>(sw + col0 + 2 * t4);
+                    const double2 u2 = *reinterpret_cast<const double2*>(su + col0 + 2 * t4);
+                    double b2[2][NQ];      // B fragments of the cross-term product: rows 2 t4 + e of the column tile
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int nq = 0; nq < NQ; ++nq) b2[e][nq] = sx[(col0 + 2 * t4 + e) * DP + 8 * nq + g];
+                    double cs0 = 0.0, cs1 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        double kap0, ew0, kap1, ew1;
+                        kappa_and_dweight<KIND, 10>(acc[i][0], s_tab, kap0, ew0);
+                        kappa_and_dweight<KIND, 10>(acc[i][1], s_tab, kap1, ew1);
+                        const double om0 = fma(hw[i], u2.x, hu[i] * w2.x);
+                        const double om1 = fma(hw[i], u2.y, hu[i] * w2.y);
+                        const double cw0 = ew0 * om0, cw1 = ew1 * om1;
+                        gvar = fma(kap0, om0, gvar);
+                        gvar = fma(kap1, om1, gvar);
+                        racc[i] = fma(rs, cw0 + cw1, racc[i]);
+                        cs0 += cw0;
+                        cs1 += cw1;
+#pragma unroll
+                        for (int nq = 0; nq < NQ; ++nq) {
+                            dmma884c(yq[i][nq], cw0, b2[0][nq], yq[i][nq][0], yq[i][nq][1]);
+                            dmma884c(yq[i][nq], cw1, b2[1][nq], yq[i][nq][0], yq[i][nq][1]);
+                        }
+                    }
+                    c8[2 * j] = cs0;
+                    c8[2 * j + 1] = cs1;
+                }
+                if (offdiag) {
+                    int cnt = 8;
+#pragma unroll
+                    for (int off = 16; off >= 4; off >>= 1, cnt >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int h = 0; h < cnt / 2; ++h) {
+                            const double send = up ? c8[h] : c8[h + cnt / 2];
+                            const double keep = up ? c8[h + cnt / 2] : c8[h];
+                            c8[h] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    const long jc = j0 + hh * 32 + (idx >> 1) * 8 + 2 * t4 + (idx & 1);
+                    if (jc < args.ncols) atomicAdd(args.y + jc, c8[0]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stage]);
+            if (++stage == DS_STAGES) { stage = 0; phase ^= 1; }
+        }
+        // item end: row sums (over the 4 lanes sharing g) and the cross term X_q = sum_i a_iq Y_iq
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            double s = racc[i];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            const long row = r0 + warp * WROWS + i * 8 + g;
+            if (t4 == 0 && live[i]) atomicAdd(args.y + row, s);
+            if (live[i]) {
+                const double* src = args.xp_rows + row * DP;
+#pragma unroll
+                for (int nq = 0; nq < NQ; ++nq)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int q = 8 * nq + 2 * t4 + e;
+                        if (q < D) gql[nq][e] = fma(-2.0 * __ldg(src + q), yq[i][nq][e], gql[nq][e]);
+                    }
+            }
+        }
+        cc.tau += gridDim.x;
+        cc.load_item(args, n_chunks);
+    }
+
+    // block reduction: slot q = 8 nq + 2 t4 + e lives in the lanes with this t4 -> sum over g (lane bits 2..4), then warps
+#pragma unroll
+    for (int nq = 0; nq < NQ; ++nq)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double s = gql[nq][e];
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            gql[nq][e] = s;
+        }
+    {
+        const double s = warp_sum(gvar);
+        if (lane == 0) s_red[warp][4 * NQ] = s;
+    }
+    // lanes 0..3 (g = 0) hold the warp sums of slots 8 nq + 2 t4 + e; slots >= D are skipped below
+    __shared__ double s_q[WARPS][8 * NQ];
+    if (g == 0) {
+#pragma unroll
+        for (int nq = 0; nq < NQ; ++nq) {
+            s_q[warp][8 * nq + 2 * t4] = gql[nq][0];
+            s_q[warp][8 * nq + 2 * t4 + 1] = gql[nq][1];
+        }
+    }
+    __syncthreads();
+    if (tid < D) {
+        double s = 0.0;
+        for (int w = 0; w < WARPS; ++w) s += s_q[w][tid];
+        atomicAdd(args.gout + tid, s);
+    } else if (tid == D) {
+        double s = 0.0;
+        for (int w = 0; w < WARPS; ++w) s += s_red[w][4 * NQ];
+        atomicAdd(args.gout + D, s);
+    }
+}
+
+template <int KIND, int D, int WARPS = 8, int MT = 4>
+static int run_dbwd(Context* ctx, SweepArgs a, cudaStream_t st) {
+    constexpr int DP = SmemLayout<D>::DP;
+    constexpr int ROWS = WARPS * 8 * MT, CHUNK = DS_RPC * ROWS, THREADS = WARPS * 32;
+    a.nb_rows = (a.nrows + ROWS - 1) / ROWS;
+    const long n_chunks = (a.ncols + CHUNK - 1) / CHUNK;
+    a.nb_cols = n_chunks;
+    a.nitems = DS_RPC * n_chunks * (n_chunks + 1) / 2;
+    auto kern = dmma_bwd_kernel<KIND, D, WARPS, MT>;
+    const size_t smem = (size_t)(DS_STAGES * kBJ * DP + DS_STAGES * 2 * kBJ) * sizeof(double) + 2 * DS_STAGES * sizeof(uint64_t);
+    CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
+    if (my_items <= 0) return CGLB_OK;
+    const int grid = (int)(my_items < ctx->num_sms ? my_items : ctx->num_sms);
+    kern<<<grid, THREADS, smem, st>>>(a, n_chunks);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
 }  // namespace cglb

@@ -185,6 +185,7 @@ int wide_bwd_sweep(Context* ctx, int kind, const double* xp, long n, int d, cons
                    double* gout, int part, int nparts, cudaStream_t st);
 
 bool dsweep_supported(const Context* ctx, int d, long n, int nparts);
+bool dbwd_supported(const Context* ctx, int d, long n, int nparts);
 
 // developer switch: CGLB_DSWEEP=0 routes every d <= 32 symmetric sweep through the register-resident kernel,
 // CGLB_DSWEEP=2 forces the DMMA sweep wherever the packed width allows it (tests of small shapes)
@@ -197,6 +198,10 @@ static int dispatch(Context* ctx, int kind, int d, int mode, const SweepArgs& a,
     if (mode == 0 && d <= CGLB_MAX_REGISTER_D) {
         const int dm = dsweep_mode();
         if (dm != 0 && dsweep_supported(ctx, d, a.nrows, dm == 2 ? 0 : a.nparts)) mode = 3;
+    }
+    if (mode == 2 && d <= CGLB_MAX_REGISTER_D) {
+        const int dm = dsweep_mode();
+        if (dm != 0 && dbwd_supported(ctx, d, a.nrows, dm == 2 ? 0 : a.nparts)) mode = 4;
     }
     if (d > CGLB_MAX_REGISTER_D && mode == 2)
         return wide_bwd_sweep(ctx, kind, a.xp_rows, a.nrows, d, a.vcol, a.ucol, a.y, a.gout, a.part, a.nparts, st);

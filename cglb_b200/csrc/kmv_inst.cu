@@ -24,6 +24,14 @@ int CGLB_CAT(sweep_d, CGLB_KMV_D)(Context* ctx, int kind, int mode, const SweepA
             return CGLB_ERR_UNSUPPORTED;
         }
     }
+    if (mode == 4) {      // symmetric backward sweep on DMMA (dsweep_impl.cuh)
+        if constexpr (D >= 2) {
+            return kind == CGLB_MATERN32 ? run_dbwd<CGLB_MATERN32, D>(ctx, a, st) : run_dbwd<CGLB_RBF, D>(ctx, a, st);
+        } else {
+            set_error("dbwd: d=%d is not instantiated", D);
+            return CGLB_ERR_UNSUPPORTED;
+        }
+    }
     if (kind == CGLB_MATERN32) {
         if (mode == 0) return run_fwd<CGLB_MATERN32, D, true>(ctx, a, st);
         if (mode == 1) return run_fwd<CGLB_MATERN32, D, false>(ctx, a, st);

@@ -249,6 +249,33 @@ def test_backward_sweep_matches_autograd(eng, kind, n, d):
     assert float((parts.cpu() - ref).norm() / ref.norm()) <= 1e-9
 
 
+@pytest.mark.parametrize("d", [2, 3, 7, 8, 10, 11, 12, 13, 16, 17, 19, 24, 27, 32])
+def test_dmma_backward_sweep_matches_autograd(eng, monkeypatch, d):
+    """K2 on DMMA (dmma_bwd_kernel): forced onto small ragged shapes; the second DMMA product (cross term) reads
+    coordinate slots past the packed row for d not a multiple of 8."""
+    monkeypatch.setenv("CGLB_DSWEEP", "2")
+    kind = "matern32" if d % 2 else "rbf"
+    n = 500 + 37 * d
+    x, v, u, ls = _problem(n, d, seed=11 * n + d)
+    dev = eng.device
+    xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    out = eng.zeros(d + 1)
+    eng.kmv_bwd_sym(kind, xp, n, d, u.to(dev), v.to(dev), 1.3, ls.to(dev), out)
+    lsr, varr = ls.clone().requires_grad_(True), torch.tensor(1.3, dtype=f64, requires_grad=True)
+    f = u @ (o.kernel_dense(kind, x, x, lsr, varr) @ v)
+    gl, gv = torch.autograd.grad(f, [lsr, varr])
+    ref = torch.cat([gl.reshape(-1), gv.reshape(1)])
+    assert float((out.cpu() - ref).abs().max() / ref.abs().max()) <= 1e-9
+    parts = eng.zeros(d + 1)
+    for p in range(3):
+        eng.kmv_bwd_sym(kind, xp, n, d, u.to(dev), v.to(dev), 1.3, ls.to(dev), parts, part=p, nparts=3)
+    assert float((parts.cpu() - ref).abs().max() / ref.abs().max()) <= 1e-9
+    monkeypatch.setenv("CGLB_DSWEEP", "0")
+    out0 = eng.zeros(d + 1)
+    eng.kmv_bwd_sym(kind, xp, n, d, u.to(dev), v.to(dev), 1.3, ls.to(dev), out0)
+    assert float((out - out0).abs().max() / out0.abs().max()) <= 1e-11
+
+
 def test_operator_protocol_with_autograd(eng):
     """`kernel(x).add_diag(s2) @ v` (models.py:251-252,280) is differentiable w.r.t. the kernel parameters."""
     x, y, z = o.synthetic_problem(400, 3, 8, seed=2)
