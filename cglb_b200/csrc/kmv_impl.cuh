@@ -3,6 +3,9 @@
 //   y = variance * K(X,X) v + diag * v          (cglb_kmv_sym, cglb_kmv_rect)
 //   d(u^T K w)/d{lengthscale, variance}          (cglb_kmv_bwd_sym)
 //
+// This file holds the register-resident DFMA sweeps (every d <= 32; the K*v sweeps of d = 10, 11, 13..32 and the
+// backward sweeps of d = 6..8, 10..32 take the DMMA kernels of dsweep_impl.cuh when the problem is large enough,
+// fp32 models the FP32-pair kernels of f32sweep_impl.cuh).
 // Replaces the KeOps Genred reductions behind `A @ p` (reference conjugate_gradient.py:57,66,72,
 // models.py:280) and their autograd (optimizer.py:97).  Design:
 //   * persistent CTAs (one per SM), 8 warps; lane 0 of warp 0 also drives the TMA ring two tiles ahead;
@@ -12,7 +15,7 @@
 //     of BJ packed rows + the matching slice of v arrive in shared memory through cp.async.bulk (TMA)
 //     on a 4-stage mbarrier ring and are read as warp-wide broadcasts;
 //   * squared distances in the expanded form |a|^2+|b|^2-2ab (d+1 DFMA-class slots instead of 2d),
-//     clamped in the integer pipe, sqrt/exp from common.cuh (5+9 slots);
+//     clamped in the integer pipe, sqrt/exp from common.cuh (5+7 slots);
 //   * column sums: transposing butterfly over groups of CG columns (9 DADD per 8 columns), then a
 //     cross-warp shared-memory reduction and one RED.ADD.F64 per column per tile.
 #pragma once
