@@ -45,7 +45,7 @@ void set_error(const char* fmt, ...);
 struct Context {
     int device;
     int num_sms;
-    // work-stealing counters for the persistent kernels (one int per launch slot)
+    // arrival counter of the two-stage deterministic reductions (vecops.cu: the last block sums in fixed order)
     int* counters;        // [16]
     // padded copies of the vector operands of the sweeps
     double* vpad;         // [vpad_cap]
@@ -125,16 +125,7 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 // ~29 FP64 issue slots; these cost 5 + 9.
 // ---------------------------------------------------------------------------------------------
 
-// clamp a (possibly slightly negative, from the expanded-form cancellation) squared distance into
-// [2^-1000, 2^60] using integer min/max on the high word -- zero FP64-pipe cost.
-__device__ __forceinline__ double clamp_sq(double q) {
-    int hi = __double2hiint(q);
-    hi = max(hi, 0x01700000);   // ~2^-1000 ; negative doubles have hi < 0 as int
-    hi = min(hi, 0x43B00000);   // 2^60
-    return __hiloint2double(hi, __double2loint(q));
-}
-
-// sqrt(q) for q in [2^-1000, 2^60]: MUFU.RSQ64H seed (rel err 2^-20, measured) + one third-order
+// sqrt(q) for q in [2^-1000, 2^60] (the callers clamp q with integer min/max on its high word, kmv_impl.cuh): MUFU.RSQ64H seed (rel err 2^-20, measured) + one third-order
 // correction: s = g(1 + e/2 + 3e^2/8), e = 1 - q y^2  -> rel err ~ (5/16) e^3 < 1e-18.  5 FP64 slots.
 __device__ __forceinline__ double fast_sqrt(double q) {
     double y;
