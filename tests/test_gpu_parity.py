@@ -92,6 +92,17 @@ def test_dmma_sweep_every_dimension(eng, monkeypatch, d):
     assert float((y.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
 
 
+def test_kmv_sym_variant_query(eng, monkeypatch):
+    """cglb_kmv_sym_variant names the kernel cglb_kmv_sym launches: 0 register DFMA, 1 DMMA-distance, 2 wide DMMA."""
+    monkeypatch.delenv("CGLB_DSWEEP", raising=False)
+    assert eng.kmv_sym_variant(11, 2000000, 1) == 1 and eng.kmv_sym_variant(11, 2000000, 8) == 1
+    assert eng.kmv_sym_variant(11, 5000, 1) == 0          # too few work items for the DMMA sweep
+    assert eng.kmv_sym_variant(3, 434000, 1) == 0 and eng.kmv_sym_variant(8, 40000, 1) == 0 and eng.kmv_sym_variant(12, 500000, 1) == 0
+    assert eng.kmv_sym_variant(90, 515000, 1) == 2
+    monkeypatch.setenv("CGLB_DSWEEP", "0")
+    assert eng.kmv_sym_variant(11, 2000000, 1) == 0
+
+
 def test_dmma_sweep_duplicates_and_midsize(eng, monkeypatch):
     dev = eng.device
     # exact duplicates: zero and slightly negative expanded-form distances
