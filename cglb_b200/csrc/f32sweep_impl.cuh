@@ -8,8 +8,11 @@
 //   column sums are reduced in FP32 inside a warp tile and leave the CTA as FP64 atomics.  Everything outside
 //   the two n^2 sweeps (K_nm, Cholesky, CG vectors, preconditioner) stays FP64.
 //
-// Packed FP32 layout (cglb_pack_inputs_f32): row i = { c (x_iq - shift_q) / l_q rounded to float (q < d), zero
+// Packed FP32 layout (cglb_pack_inputs_f32): row i = { c' (x_iq - shift_q) / l_q rounded to float (q < d), zero
 // padding, |.|^2 of the ROUNDED coordinates in the last slot }, width DPF = d + 1 rounded up to a multiple of 4.
+// c' folds the base-2 conversion of the exponential into the inputs: Matern32 c' = sqrt(3) log2(e), so that
+// sqrt(q) = s log2(e) feeds MUFU.EX2 directly and kappa = e + ln2 (s' e); RBF c' = sqrt(log2(e) / 2), so that
+// e^{-r^2/2} = 2^{-q}.  One FMUL less per pair than scaling inside the loop; MUFU.SQRT replaces RSQ + FMUL.
 // Same work decomposition, TMA ring and symmetric-pair trick as kmv_sweep_kernel (kmv_impl.cuh).
 #pragma once
 #include <stdlib.h>
@@ -31,19 +34,22 @@ struct SweepArgsF32 {
     int part, nparts;
 };
 
+// scale of the packed fp32 coordinates relative to the fp64 packing (see the header comment)
+__host__ __device__ inline double f32_input_scale(int kind) {
+    return kind == CGLB_MATERN32 ? 1.4426950408889634074 : 1.2011224087864498;      // log2(e), sqrt(log2(e))
+}
+
 template <int KIND>
 __device__ __forceinline__ float kappa_f32(float q) {
+    q = fmaxf(q, 0.0f);                          // cancellation of the expanded form / the diagonal
     if (KIND == CGLB_MATERN32) {
-        q = fmaxf(q, 1e-30f);                    // cancellation of the expanded form / the diagonal
-        float y;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(q));
-        const float s = q * y;
-        float e;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(s * -1.4426950408889634f));
-        return fmaf(s, e, e);
+        float s, e;                              // s = sqrt(3) r log2(e)
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(q));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-s));
+        return fmaf(s * e, 0.69314718055994531f, e);
     } else {
         float e;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaxf(q, 0.0f) * -1.4426950408889634f));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q));
         return e;
     }
 }
@@ -233,15 +239,14 @@ struct BwdArgsF32 {
 
 template <int KIND>
 __device__ __forceinline__ void kappa_dweight_f32(float q, float& kap, float& ew) {
+    q = fmaxf(q, 0.0f);
     if (KIND == CGLB_MATERN32) {
-        q = fmaxf(q, 1e-30f);
-        float y;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(q));
-        const float s = q * y;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ew) : "f"(s * -1.4426950408889634f));
-        kap = fmaf(s, ew, ew);
+        float s;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(q));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ew) : "f"(-s));
+        kap = fmaf(s * ew, 0.69314718055994531f, ew);
     } else {
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ew) : "f"(fmaxf(q, 0.0f) * -1.4426950408889634f));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ew) : "f"(-q));
         kap = ew;
     }
 }
@@ -306,6 +311,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) f32_bwd_kernel(const BwdArgsF32
     double gq[D], gvar = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) gq[k] = 0.0;
+    const double inv_scale_sq = 1.0 / (f32_input_scale(KIND) * f32_input_scale(KIND));
 
     while (cc.valid) {
         const bool offdiag = cc.I != cc.C;
@@ -392,7 +398,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) f32_bwd_kernel(const BwdArgsF32
 #pragma unroll
             for (int ti = 0; ti < TI; ++ti) racc[ti] += (double)rt[ti];
 #pragma unroll
-            for (int k = 0; k < D; ++k) gq[k] += (double)gqt[k];
+            for (int k = 0; k < D; ++k) gq[k] = fma((double)gqt[k], inv_scale_sq, gq[k]);    // a_i a_j carries scale^2
             gvar += (double)gvt;
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[stage]);

@@ -38,7 +38,8 @@ __global__ void pack_inputs_f32_kernel(int kind, const double* __restrict__ x, l
         for (int k = 0; k < dpf; ++k) o[k] = 0.0f;
         return;
     }
-    const double c = (kind == CGLB_MATERN32) ? 1.7320508075688772935 : 0.70710678118654752440;
+    // the fp64 scaling times the base-2 factor of f32sweep_impl.cuh (the exponentials run on MUFU.EX2)
+    const double c = ((kind == CGLB_MATERN32) ? 1.7320508075688772935 : 0.70710678118654752440) * f32_input_scale(kind);
     double nrm = 0.0;
     for (int k = 0; k < d; ++k) {
         const float a = (float)(c * (x[i * d + k] - (shift ? shift[k] : 0.0)) / ls[k]);

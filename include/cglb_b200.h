@@ -83,7 +83,7 @@ CGLB_API int cglb_kmv_sym_variant(const cglb_context* ctx, int d, long n, int np
  * Same product as cglb_kmv_sym with the n^2 kernel-pair evaluations in FP32 (FP32 FMA pipe + MUFU rsqrt/ex2);
  * v, y and all accumulation across tiles stay FP64.  Per-entry error ~1e-6 (expanded-form distances in
  * fp32), d <= 32.  xpf comes from cglb_pack_inputs_f32: width cglb_packed_width_f32(d) floats,
- * cglb_padded_rows(n) rows.
+ * cglb_padded_rows(n) rows (coordinates additionally scaled by log2(e) resp. sqrt(log2(e)): opaque to callers).
  * replaces: the same call sites as cglb_kmv_sym when the model was created under set_default_float("fp32"). */
 CGLB_API int cglb_packed_width_f32(int d);
 CGLB_API int cglb_pack_inputs_f32(cglb_context* ctx, int kind, const double* x, long n, int d, const double* lengthscale,
