@@ -25,7 +25,10 @@ def _declared_symbols():
 def test_header_symbols_are_exported_and_bound(lib):
     from cglb_b200 import _ffi
     declared = _declared_symbols()
-    assert len(declared) >= 26
+    assert len(declared) >= 31
+    for must in ("cglb_kmv_sym", "cglb_kmv_bwd_sym", "cglb_kmv_sym_f32", "cglb_kmv_bwd_sym_f32", "cglb_pack_inputs_f32",
+                 "cglb_kmv_sym_variant", "cglb_potrf", "cglb_precond_project", "cglb_cg_step"):
+        assert must in declared
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/cglb_b200.h but not exported"
         assert name in _ffi.SIGNATURES, f"{name} has no ctypes signature in cglb_b200/_ffi.py"
@@ -36,6 +39,12 @@ def test_abi_helpers_without_gpu(lib):
     assert lib.cglb_abi_version() == 1
     assert lib.cglb_packed_width(11) == 12 and lib.cglb_packed_width(8) == 10 and lib.cglb_packed_width(1) == 2
     assert lib.cglb_padded_rows(300) == 384 and lib.cglb_padded_rows(128) == 128 and lib.cglb_padded_rows(0) == 0
+    # d > 32: wide DMMA layout (coordinates padded to a multiple of 4, row pitch = 4 or 12 mod 16)
+    assert lib.cglb_packed_width(90) == 100 and lib.cglb_packed_width(33) == 44 and lib.cglb_packed_width(64) == 68
+    # fp32-pair layout: d + 1 floats rounded up to 16 bytes
+    assert [lib.cglb_packed_width_f32(d) for d in (1, 3, 4, 8, 11, 12, 32)] == [4, 4, 8, 12, 12, 16, 36]
+    # queries with a null context fail with a status, never crash
+    assert lib.cglb_kmv_sym_variant(None, 11, 1000, 1) < 0
 
 
 def test_no_cpu_fallback(lib):
