@@ -75,6 +75,39 @@ def run_case(cg, models, name, kind, n, d, M, noise, variance, ls, mean_c, mults
           f"cg_steps={[out[f'cg_steps_{e}'] for e in range(len(mults))]}")
 
 
+# fp32 mode of the reference (interface.py:94-104, jitter 1e-5 per backend.py:76-79): the same verbatim code on
+# float32 tensors.  name, kind, n, d, M, noise, variance, lengthscale, mean_c, seed
+FP32_CASES = [
+    ("kin_like_rbf_fp32", "rbf", 400, 8, 48, 0.05, 0.9, 2.0, 0.0, 21),
+    ("house_like_matern_fp32", "matern32", 600, 11, 64, 0.05, 1.0, 1.66, 0.1, 22),
+]
+
+
+def run_case_fp32(models, name, kind, n, d, M, noise, variance, ls, mean_c, seed):
+    from . import gpytorch_stub as gp
+    x, y, z = o.synthetic_problem(n, d, M, seed=seed)
+    x32, y32, z32 = x.float(), y.float(), z.float()
+    lik = gp.GaussianLikelihood(noise_constraint=gp.GreaterThan(1e-6)).float()
+    lik.noise = noise
+    base = (gp.MaternKernel(nu=1.5, ard_num_dims=d) if kind == "matern32" else gp.RBFKernel(ard_num_dims=d)).float()
+    base.lengthscale = torch.full((d,), float(ls), dtype=torch.float32)
+    scale = gp.ScaleKernel(base).float()
+    scale.outputscale = variance
+    model = models.CGLB((x32, y32.reshape(-1)), lik, gp.InducingPointKernel(scale, z32, likelihood=lik))
+    model.mean_module = model.mean_module.float()
+    model.mean_module.constant.data.fill_(mean_c)
+    params = list(model.parameters())
+    loss = -models.LowerBoundCG(model)((x32, y32))
+    grads = torch.autograd.grad(loss, params)
+    out = dict(kind=kind, x=x32.numpy(), y=y32.numpy(), z=z32.numpy(), noise=noise, variance=variance,
+               lengthscale=np.full(d, ls, dtype=np.float32), mean_c=mean_c, jitter=1e-5,
+               loss_0=loss.detach().numpy(), cg_steps_0=int(model.cg_stats.steps))
+    for gname, g in zip(["raw_noise", "mean_constant", "inducing_points", "raw_outputscale", "raw_lengthscale"], grads):
+        out[f"grad_{gname}_0"] = g.detach().numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **out)
+    print(f"{name}: loss={float(loss)} cg_steps={int(model.cg_stats.steps)} dtype={loss.dtype}")
+
+
 def run_cg_case(cg):
     """Verbatim ConjugateGradient + NystromPreconditioner on a dense SPD system with explicit A, LB."""
     g = torch.Generator().manual_seed(77)
@@ -109,6 +142,10 @@ def main():
     run_cg_case(cg)
     for case in CASES:
         run_case(cg, models, *case)
+    rl.load(jitter=1e-5)             # the reference's fp32 jitter
+    for case in FP32_CASES:
+        run_case_fp32(models, *case)
+    rl.load(jitter=1e-6)
 
 
 if __name__ == "__main__":

@@ -355,6 +355,32 @@ def test_bound_and_gradients_match_reference_golden(name):
                 assert np.abs(gr.cpu().numpy() - refg).max() <= 5e-6 * np.abs(refg).max() + 1e-9, (name, e, nm)
 
 
+@pytest.mark.parametrize("name", ["kin_like_rbf_fp32", "house_like_matern_fp32"])
+def test_fp32_mode_matches_reference_fp32_golden(name):
+    """The reference's own LowerBoundCG run on float32 tensors (oracle/make_golden.py: FP32_CASES, jitter 1e-5)
+    against an fp32 model here (FP32 kernel pairs, FP64 accumulation and linear algebra).  The reference's fp32 run
+    is itself ~3e-6 away from its fp64 run on the bound and ~1e-4 on the gradients: tolerances 2e-5 / 1e-3."""
+    from cglb_b200 import settings
+    g = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    kind = str(g["kind"])
+    old = settings.cholesky_jitter.value()
+    settings.cholesky_jitter._set_value(float(g["jitter"]))
+    try:
+        model = make_model(kind, g["x"], g["y"], g["z"], float(g["noise"]), float(g["variance"]), g["lengthscale"],
+                           float(g["mean_c"]), dtype=torch.float32)
+        assert model.train_inputs[0].dtype == torch.float32
+        loss = -cb.LowerBoundCG(model)((model.train_inputs[0], model.train_targets))
+        grads = torch.autograd.grad(loss, list(model.parameters()))
+        ref = float(g["loss_0"])
+        assert loss.dtype == torch.float32 and abs(float(loss) - ref) <= 2e-5 * abs(ref)
+        assert abs(int(model.cg_stats.steps) - int(g["cg_steps_0"])) <= 1
+        for nm, gr in zip(GRAD_NAMES, grads):
+            refg = g[f"grad_{nm}_0"]
+            assert np.abs(gr.cpu().numpy() - refg).max() <= 1e-3 * np.abs(refg).max() + 1e-6, (name, nm)
+    finally:
+        settings.cholesky_jitter._set_value(old)
+
+
 @pytest.mark.parametrize("kind,n,d,M,noise", [("matern32", 900, 3, 40, 0.05), ("rbf", 700, 8, 33, 0.3), ("matern32", 513, 11, 64, 0.01),
                                               ("matern32", 400, 20, 24, 0.1), ("matern32", 1200, 90, 48, 0.05), ("rbf", 700, 40, 17, 0.2)])
 def test_bound_and_gradients_fixed_v_match_oracle(kind, n, d, M, noise):
