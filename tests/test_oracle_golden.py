@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import cglb_oracle as o
-from conftest import GOLDEN_CASES, GOLDEN_DIR, GRAD_NAMES
+from conftest import GOLDEN_CASES, GOLDEN_DIR, GOLDEN_FP32_CASES, GRAD_NAMES
 
 f64 = torch.float64
 
@@ -55,6 +55,24 @@ def test_bound_and_grads_match_reference_golden(name):
         for gname, gr in zip(GRAD_NAMES, grads):
             ref = g[f"grad_{gname}_{e}"]
             assert np.abs(gr.numpy() - ref).max() <= 1e-7 * np.abs(ref).max() + 1e-9, gname
+
+
+@pytest.mark.parametrize("name", GOLDEN_FP32_CASES)
+def test_fp32_golden_is_consistent_with_the_fp64_oracle(name):
+    """The fp32 golden vectors (the reference's own code on float32 tensors, jitter 1e-5) against the fp64 oracle on
+    the same (float32-rounded) inputs: the reference's fp32 arithmetic is ~3e-6 away on the bound and ~2e-4 on the
+    gradients, and takes the same number of CG iterations (+-1)."""
+    g = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    assert g["x"].dtype == np.float32 and g["loss_0"].dtype == np.float32
+    kind = str(g["kind"])
+    x, y, z = (torch.from_numpy(g[k]).double() for k in ("x", "y", "z"))
+    p = o.OracleParams.from_values(float(g["noise"]), float(g["mean_c"]), z, float(g["variance"]), g["lengthscale"].astype(np.float64))
+    loss, grads, res = o.bound_and_grads(kind, p, x, y, torch.zeros(x.shape[0], 1, dtype=f64), jitter=float(g["jitter"]))
+    assert abs(float(loss) - float(g["loss_0"])) <= 2e-5 * abs(float(loss))
+    assert abs(res.cg.steps - int(g["cg_steps_0"])) <= 1
+    for gname, gr in zip(GRAD_NAMES, grads):
+        ref = g[f"grad_{gname}_0"]
+        assert np.abs(gr.numpy() - ref).max() <= 1e-3 * np.abs(gr.numpy()).max() + 1e-6, gname
 
 
 @pytest.mark.parametrize("name", ["road_like_trained", "kin_like_rbf"])
