@@ -303,6 +303,8 @@ def run_b200(args, rank, world, local_rank):
     kmv_ms = float(kt[0]) / max(n_kmv, 1)
     achieved = fpp * float(n) * n / world / (kmv_ms * 1e-3) / 1e12 if n_kmv else None
     ncu = load_json(os.path.join(ROOT, "profiles", "kmv_ncu_summary.json")) or {}
+    # DRAM bytes per launch (ncu, per rank): every rank streams the whole packed input array once, whatever its share of
+    # the work items, so the single-GPU figure holds for every N
     traffic = ncu.get(f"{args.workload}", {}).get("dram_bytes_per_launch")
     variant = eng.kmv_sym_variant(d, n, world)
     diag_block = {0: 1024.0, 1: 256.0, 2: 128.0}[variant]      # rows of the diagonal blocks, evaluated as full squares
