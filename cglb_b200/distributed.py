@@ -2,7 +2,8 @@
 
 One process per GPU (`torch.distributed`, NCCL over NVLink 5 / NVSwitch).  What is sharded:
   * the work items of the matrix-free sweeps (K v, backward sweep): rank g processes the tile pairs
-    {t : t % world == g} of the symmetric enumeration (csrc/kmv_impl.cuh) and the partial n-vectors are
+    {t : t % world == g} of the symmetric enumeration (square blocks in csrc/kmv_impl.cuh, row-block x
+    column-chunk strips in csrc/dsweep_impl.cuh; `symmetric_items` / `strip_items` below) and the partial n-vectors are
     all-reduced -- with the symmetric sweep a tile contributes to two row blocks, so the exchange is an
     all-reduce of y rather than an all-gather of p;
   * the columns of the dense M x n matrix A = L^-1 K_uf / sigma (rows of K_nm): rank g owns the
@@ -79,3 +80,26 @@ def symmetric_items(n: int, block: int):
         for i in range(c + 1):
             yield t, i, c
             t += 1
+
+
+def strip_items(n: int, rows: int = 256, rows_per_chunk: int = 4, tile: int = 64):
+    """Enumeration of the DMMA sweeps' work items (DCursor in csrc/dsweep_impl.cuh): item t = rows_per_chunk *
+    C (C + 1) / 2 + I pairs the row block I (`rows` rows) with the column chunk C (`rows_per_chunk * rows`
+    columns), for every I < rows_per_chunk (C + 1) that exists; only the columns at or after the row block are
+    visited, in tiles of `tile` columns.  Yields (t, r0, r1, [(j0, j1, offdiag), ...]): tiles overlapping the row
+    block (offdiag False) are evaluated as ordered pairs and feed the row sums only, tiles beyond it feed the row
+    AND the column sums."""
+    chunk = rows_per_chunk * rows
+    nb_rows = -(-n // rows)
+    n_chunks = -(-n // chunk)
+    for c in range(n_chunks):
+        for i in range(rows_per_chunk * (c + 1)):
+            t = rows_per_chunk * c * (c + 1) // 2 + i
+            if i >= nb_rows:
+                continue
+            r0 = i * rows
+            cbeg, cend = max(c * chunk, r0), min((c + 1) * chunk, n)
+            if cbeg >= cend:
+                continue
+            tiles = [(j0, min(j0 + tile, cend), j0 >= r0 + rows) for j0 in range(cbeg, cend, tile)]
+            yield t, r0, min(r0 + rows, n), tiles

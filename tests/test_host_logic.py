@@ -102,3 +102,35 @@ def test_shard_column_blocks_partition_and_items():
     assert [t for t, _, _ in items] == list(range(10))
     owned = [sum(Shard(r, 3).owns_item(t) for r in range(3)) for t, _, _ in items]
     assert owned == [1] * 10
+
+
+def test_strip_items_cover_every_pair_once():
+    """The DMMA sweeps' decomposition (strip_items mirrors DCursor in dsweep_impl.cuh): emulating what the kernel does
+    with each item -- ordered pairs with row sums only on the tiles overlapping the row block, row AND column sums
+    beyond it -- reproduces K v exactly, for any split of the items over ranks."""
+    import numpy as np
+    from cglb_b200.distributed import Shard, strip_items
+    rng = np.random.default_rng(0)
+    for n, rows, rpc, tile in [(700, 64, 4, 16), (1030, 128, 4, 64), (257, 256, 4, 64), (64, 16, 2, 8), (999, 32, 4, 8)]:
+        a = rng.standard_normal((n, n))
+        K = a + a.T                                   # any symmetric matrix
+        v = rng.standard_normal(n)
+        ref = K @ v
+        for world in (1, 3):
+            y = np.zeros(n)
+            seen = set()
+            for rank in range(world):
+                sh = Shard(rank, world)
+                for t, r0, r1, tiles in strip_items(n, rows, rpc, tile):
+                    if not sh.owns_item(t):
+                        continue
+                    assert t not in seen
+                    seen.add(t)
+                    for j0, j1, offdiag in tiles:
+                        blk = K[r0:r1, j0:j1]
+                        y[r0:r1] += blk @ v[j0:j1]
+                        if offdiag:
+                            y[j0:j1] += blk.T @ v[r0:r1]
+                        else:
+                            assert j0 >= r0 and j1 <= r0 + rows      # inside the diagonal block: ordered pairs
+            assert np.allclose(y, ref, rtol=1e-12, atol=1e-10), (n, rows, world)
