@@ -141,7 +141,8 @@ __device__ __forceinline__ double fast_sqrt(double q) {
 // polynomial, 2^(n/2^TB) from a 2^TB-entry table in shared memory and an exponent-field add.
 //   TB = 6  : 64-entry table, degree-5 polynomial, 9 FP64 slots  (small kernels: 512 B of shared memory)
 //   TB = 10 : 1024-entry table (8 KB), degree-3 polynomial with the r^4/24 term folded into the quadratic
-//             coefficient (Chebyshev), 7 FP64 slots, max rel. error 7e-17 + rounding      (the sweeps)
+//             coefficient (Chebyshev), 7 FP64 slots, max rel. error 9.4e-17 + rounding    (the sweeps;
+//             checked in 50-digit arithmetic by tests/test_kernel_arithmetic.py)
 // The caller clamps s to [0, 693] (kappa() does it on the squared distance with two integer min/max), so
 // e^-s >= 2^-1000 and the exponent-field add cannot wrap: no separate exponent clamp.
 // Instruction diet (profiles/README_r02.md): every non-FP64 instruction costs the FP64 pipe ~1 issue cycle in
@@ -165,7 +166,8 @@ __device__ __forceinline__ double fast_exp_neg(double s, const double* __restric
         p = fma(p, r, 0.5);
         p = fma(p, r, 1.0);
     } else {
-        p = fma(r, 1.6666666666666665741e-01, 0.5 + 4.7730e-09);      // 1/2 + h^2/24, h = ln2/2048
+        p = fma(r, 1.6666666666666665741e-01, 0.5 + 3.9540e-09);      // 1/2 + (sqrt2 - 1) h^2 / 12, h = ln2/2048: the
+                                                                       // r^4/24 term equioscillates, max rel. err 9.4e-17
         p = fma(p, r, 1.0);
     }
     double T = tab[n & ((1 << TB) - 1)];

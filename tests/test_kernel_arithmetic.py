@@ -1,0 +1,82 @@
+"""CPU: the numerical claims behind the hand-written sqrt / exp of the sweeps (cglb_b200/csrc/common.cuh), checked in
+50-digit decimal arithmetic with the constants parsed from the CUDA source, so that the test follows the kernels:
+  * exp: r = -s - n ln2/2^TB with n = rint(-s 2^TB/ln2), e^r by the short polynomial, 2^(n/2^TB) from a table;
+  * sqrt: MUFU.RSQ64H seed (relative error <= 2^-20, measured) + one third-order correction."""
+import os
+import re
+from decimal import Decimal, getcontext
+
+getcontext().prec = 50
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = open(os.path.join(ROOT, "cglb_b200", "csrc", "common.cuh")).read()
+LN2 = Decimal(2).ln()
+
+
+def _const(pattern):
+    m = re.search(pattern, SRC)
+    assert m, pattern
+    return [Decimal(g) for g in m.groups()]
+
+
+def test_exp_reduction_constants_are_consistent():
+    c6, c10 = _const(r"constexpr double C = \(TB == 6\) \? ([0-9.e+-]+) : ([0-9.e+-]+);")
+    l6, l10 = _const(r"constexpr double L = \(TB == 6\) \? ([0-9.e+-]+) : ([0-9.e+-]+);")
+    for tb, c, l in ((6, c6, l6), (10, c10, l10)):
+        assert abs(c - Decimal(2) ** tb / LN2) / c < Decimal("2e-16")          # 2^TB / ln 2 to double precision
+        assert abs(l - LN2 / Decimal(2) ** tb) / l < Decimal("2e-16")          # ln 2 / 2^TB
+    # the magic number 1.5 * 2^52 makes `t - MAGIC` exact and leaves n in the low word for |n| < 2^31
+    (magic,) = _const(r"const double MAGIC = ([0-9.]+);")
+    assert magic == Decimal(3) * Decimal(2) ** 51
+
+
+def _max_rel_err(poly, h, samples=2001):
+    worst = Decimal(0)
+    for i in range(samples):
+        r = -h + 2 * h * Decimal(i) / Decimal(samples - 1)
+        worst = max(worst, abs(poly(r) - r.exp()) / r.exp())
+    return worst
+
+
+def test_exp_polynomials_reach_double_precision_on_their_intervals():
+    # TB = 10: p = c3 r + (1/2 + eps); p = p r + 1; e^r = 1 + r p      on |r| <= ln2 / 2^11 (n is the nearest integer)
+    c3, c2a, c2b = _const(r"p = fma\(r, ([0-9.e+-]+), ([0-9.e+-]+) \+ ([0-9.e+-]+)\);")
+    h10 = LN2 / Decimal(2) ** 11
+    err10 = _max_rel_err(lambda r: 1 + r * ((c3 * r + (c2a + c2b)) * r + 1), h10)
+    assert err10 < Decimal("1e-16"), err10
+    # without the Chebyshev shift of the quadratic coefficient the truncation error would be r^4/24 = 5.4e-16
+    err_plain = _max_rel_err(lambda r: 1 + r * ((c3 * r + c2a) * r + 1), h10)
+    assert err_plain > 3 * err10
+    # TB = 6: degree 5 in r after the leading 1 on |r| <= ln2 / 2^7
+    c5, c4 = _const(r"p = fma\(r, ([0-9.e+-]+), ([0-9.e+-]+)\);\s*\n\s*p = fma\(p, r, 1\.6666")
+    (c3b,) = _const(r"p = fma\(p, r, (1\.6666[0-9.e+-]+)\);")
+    h6 = LN2 / Decimal(2) ** 7
+    err6 = _max_rel_err(lambda r: 1 + r * ((((c5 * r + c4) * r + c3b) * r + Decimal("0.5")) * r + 1), h6)
+    assert err6 < Decimal("1e-16"), err6
+
+
+def test_sqrt_third_order_correction():
+    # y = (1 + delta) / sqrt(q), |delta| <= 2^-20 (measured for rsqrt.approx.ftz.f64):
+    # g = q y, e = 1 - g y, s = g + g e (1/2 + 3/8 e)  ->  relative error ~ (5/16) e^3 << 2^-53
+    for q in (Decimal("1e-12"), Decimal("0.3"), Decimal(7), Decimal("480000")):
+        for k in range(-8, 9):
+            delta = Decimal(k) / 8 * Decimal(2) ** -20
+            y = (1 + delta) / q.sqrt()
+            g = q * y
+            e = 1 - g * y
+            s = g + g * (e * (Decimal("0.375") * e + Decimal("0.5")))
+            assert abs(s - q.sqrt()) / q.sqrt() < Decimal("1e-17")
+
+
+def test_clamp_keeps_the_exponent_field_in_range():
+    # kappa() clamps s <= 693 (q <= 693^2 resp. 693) so that e^-s >= 2^-1000: the exponent-field add of fast_exp_neg
+    # (res in [1, 2) scaled by 2^m, m = n >> TB >= -1000) stays in the normal range
+    kern = open(os.path.join(ROOT, "cglb_b200", "csrc", "kmv_impl.cuh")).read()
+    hi_m = int(re.search(r"kClampHiMatern = (0x[0-9a-fA-F]+);", kern).group(1), 16)
+    hi_r = int(re.search(r"kClampHiRbf = (0x[0-9a-fA-F]+);", kern).group(1), 16)
+    import struct
+    qm = struct.unpack(">d", struct.pack(">II", hi_m, 0xFFFFFFFF))[0]      # largest double with this high word
+    qr = struct.unpack(">d", struct.pack(">II", hi_r, 0xFFFFFFFF))[0]
+    for s_max in (qm ** 0.5, qr):
+        assert s_max < 693.01
+        m = int(-s_max / 0.6931471805599453) - 1
+        assert m >= -1001 and 1023 + m > 0
