@@ -24,6 +24,11 @@ def test_exp_reduction_constants_are_consistent():
     for tb, c, l in ((6, c6, l6), (10, c10, l10)):
         assert abs(c - Decimal(2) ** tb / LN2) / c < Decimal("2e-16")          # 2^TB / ln 2 to double precision
         assert abs(l - LN2 / Decimal(2) ** tb) / l < Decimal("2e-16")          # ln 2 / 2^TB
+    # ln2/2^TB is ONE double (no hi/lo split): its representation error delta_L puts s * delta_L into r, i.e. a relative
+    # error of s * 3.3e-17 on e^-s (1e-15 at s = 30) -- the dominant term of the kernel map's error, far inside the 1e-10
+    # per-matvec tolerance
+    assert abs(Decimal(float(l10)) - LN2 / Decimal(2) ** 10) / (LN2 / Decimal(2) ** 10) < Decimal("4e-17")
+    assert abs(Decimal(float(l6)) - LN2 / Decimal(2) ** 6) / (LN2 / Decimal(2) ** 6) < Decimal("4e-17")
     # the magic number 1.5 * 2^52 makes `t - MAGIC` exact and leaves n in the low word for |n| < 2^31
     (magic,) = _const(r"const double MAGIC = ([0-9.]+);")
     assert magic == Decimal(3) * Decimal(2) ** 51
