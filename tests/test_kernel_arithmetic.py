@@ -25,8 +25,8 @@ def test_exp_reduction_constants_are_consistent():
         assert abs(c - Decimal(2) ** tb / LN2) / c < Decimal("2e-16")          # 2^TB / ln 2 to double precision
         assert abs(l - LN2 / Decimal(2) ** tb) / l < Decimal("2e-16")          # ln 2 / 2^TB
     # ln2/2^TB is ONE double (no hi/lo split): its representation error delta_L puts s * delta_L into r, i.e. a relative
-    # error of s * 3.3e-17 on e^-s (1e-15 at s = 30) -- the dominant term of the kernel map's error, far inside the 1e-10
-    # per-matvec tolerance
+    # error of s * 3.3e-17 on e^-s (1e-15 at s = 30) -- next to the s * 1.1e-16 .. 2.2e-16 that the rounding of s itself costs any
+    # fp64 evaluation, and far inside the 1e-10 per-matvec tolerance
     assert abs(Decimal(float(l10)) - LN2 / Decimal(2) ** 10) / (LN2 / Decimal(2) ** 10) < Decimal("4e-17")
     assert abs(Decimal(float(l6)) - LN2 / Decimal(2) ** 6) / (LN2 / Decimal(2) ** 6) < Decimal("4e-17")
     # the magic number 1.5 * 2^52 makes `t - MAGIC` exact and leaves n in the low word for |n| < 2^31
@@ -85,3 +85,56 @@ def test_clamp_keeps_the_exponent_field_in_range():
         assert s_max < 693.01
         m = int(-s_max / 0.6931471805599453) - 1
         assert m >= -1001 and 1023 + m > 0
+
+
+def _fma(a, b, c):
+    """exact fused multiply-add in double precision (the DFMA of the kernels): one rounding of the exact a*b + c."""
+    from fractions import Fraction
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def test_kernel_map_end_to_end_in_emulated_fp64():
+    """kappa(q) = (1 + s) e^-s, s = sqrt(q), step by step as common.cuh / kmv_impl.cuh compute it (exact FMA emulation,
+    a 20-bit reciprocal-square-root seed with a zero low word, the 1024-entry table), against 50-digit arithmetic:
+    the relative error stays below s * 2.6e-16 + 4e-16 over the whole clamped range. The s-proportional term is the
+    rounding of s itself (the corrected sqrt is faithful, |delta s| < ulp(s) <= s * 2.2e-16, against s * 1.1e-16 for a
+    correctly rounded one -- a term ANY fp64 evaluation that forms s as a double pays, torch's included) plus the representation error of the single-double ln2/2^TB (s * 3.3e-17)."""
+    import math
+    import random
+    import struct
+    c10 = float(_const(r"constexpr double C = \(TB == 6\) \? [0-9.e+-]+ : ([0-9.e+-]+);")[0])
+    l10 = float(_const(r"constexpr double L = \(TB == 6\) \? [0-9.e+-]+ : ([0-9.e+-]+);")[0])
+    c3, c2a, c2b = (float(v) for v in _const(r"p = fma\(r, ([0-9.e+-]+), ([0-9.e+-]+) \+ ([0-9.e+-]+)\);"))
+    magic = 6755399441055744.0
+    table = [float(Decimal(2) ** (Decimal(j) / 1024)) for j in range(1024)]      # correctly rounded 2^(j/1024)
+    rnd = random.Random(0)
+    worst = 0.0
+    for _ in range(3000):
+        q = math.exp(rnd.uniform(math.log(1e-8), math.log(480000.0)))
+        # seed: relative error <= 2^-20, only the high word is produced (MUFU.RSQ64H), low word zero
+        y = (1.0 + rnd.uniform(-1, 1) * 2.0 ** -20) / math.sqrt(q)
+        y = struct.unpack(">d", struct.pack(">Q", struct.unpack(">Q", struct.pack(">d", y))[0] & 0xFFFFFFFF00000000))[0]
+        g = q * y
+        e = _fma(-g, y, 1.0)
+        p = _fma(e, 0.375, 0.5)
+        t = e * p
+        s = _fma(g, t, g)
+        assert abs(Decimal(s) - Decimal(q).sqrt()) < Decimal(math.ulp(s))          # faithful
+        # exp(-s)
+        tt = _fma(s, -c10, magic)
+        n = struct.unpack(">q", struct.pack(">d", tt))[0] & 0xFFFFFFFF
+        n = n - (1 << 32) if n >= (1 << 31) else n
+        nf = tt - magic
+        assert nf == float(n)
+        r = _fma(nf, -l10, -s)
+        pp = _fma(r, c3, c2a + c2b)
+        pp = _fma(pp, r, 1.0)
+        res = table[n & 1023] * _fma(r, pp, 1.0)
+        ex = math.ldexp(res, n >> 10)
+        kap = _fma(s, ex, ex)
+        sq = Decimal(q).sqrt()
+        ref = (1 + sq) * (-sq).exp()
+        err = float(abs(Decimal(kap) - ref) / ref)
+        assert err <= float(sq) * 2.6e-16 + 4e-16, (q, err)
+        worst = max(worst, err / (float(sq) * 2.6e-16 + 4e-16))
+    assert worst > 0.05          # the bound is not vacuous
