@@ -321,7 +321,9 @@ def run_b200(args, rank, world, local_rank):
                                ("" if args.float_type == "fp64" else " -- run in the fp32 mode of the API, NOT the fp64 metric of BASELINE.json"),
                    "theta": args.theta, "kernel": kind, "n": n, "d": d, "M": M, "parallelism": f"row-sharded x{world}",
                    "cg": "reference defaults (max_error=1, max_cg_iter=100, restart=40), warm start carried across steps, "
-                         "lengthscales perturbed by (1, 1.01, 0.99) per step",
+                         "lengthscales perturbed by (1, 1.01, 0.99) per step; K v, r and P r after the solve come from the final "
+                         "CG state (k + 1 + floor(k/40) sweeps per step; the reference recomputes them for its autograd tape: "
+                         "k + 2 + floor(k/40); CGLB_RECOMPUTE_RESIDUAL=1 selects that)",
                    "cg_steps": [s["cg"] for s in stats], "kv_sweeps_per_step": [s["matvecs"] for s in stats],
                    "loss": [s["loss"] for s in stats],
                    "l2": "inputs larger than L2 (X packed %.0f MB, A %.1f GB per rank)" % (n * (d + 2) * 8 / 1e6, M * n / world * 8 / 1e9)},
@@ -389,7 +391,10 @@ def cpu_baseline(kind, n, d, M, th, stats):
         o.blocked_matvec_rows(kind, x, v, ls, var, (reps * rows) % max(1, n - rows), rows)
         reps += 1
     per_matvec = (time.perf_counter() - t0) / reps * (n / rows)
-    sweeps = float(np.mean([s["matvecs"] for s in stats])) + 2.0 if stats else 8.0    # + autograd backward of cov@v
+    # the reference's own count: k + 2 + floor(k/40) forward sweeps (conjugate_gradient.py:57,66,72; models.py:280)
+    # + the autograd backward of cov@v (~2 more n^2 d sweeps) -- not this implementation's count, which reuses the
+    # CG residual instead of the sweep of models.py:280
+    sweeps = float(np.mean([s["cg"] + 2 + s["cg"] // 40 for s in stats])) + 2.0 if stats else 8.0
     return {"value": sweeps * per_matvec, "unit": "s/step", "cores": threads, "kind": "port",
             "sample": f"{reps} x {rows} rows x {n} cols of the oracle's row-blocked K v (torch fp64, {threads} threads), "
                       f"extrapolated to n^2 pairs x {sweeps:g} sweeps/step; Nystrom terms not included",

@@ -14,6 +14,7 @@ the reference (cglb/backend/pytorch/models.py:151-286, optimizer.py:95-98):
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -100,6 +101,8 @@ class BoundEvaluator:
         self._T = None
         self.terms: Optional[CommonTermsDev] = None
         self._packed_key = None
+        # False: recompute K v, r and P r after the CG solve as models.py:280-282 does (one more n^2 sweep)
+        self.reuse_cg_state = os.environ.get("CGLB_RECOMPUTE_RESIDUAL", "0") in ("", "0")
 
     def refresh_data(self, x: Tensor, y: Tensor):
         """New contents for the same problem shape (workspaces are kept)."""
@@ -166,18 +169,34 @@ class BoundEvaluator:
         op = self.operator(kind, variance, noise)
         precon = self.preconditioner(terms, noise)
         err = (self.y - mean_c).reshape(-1, 1)                                          # models.py:253-254
-        cg_stats = None
+        cg_stats, state = None, None
         if use_cached_v:
             v = v_vec
         else:
-            v, cg_stats = cg_opt(op, err, v_vec, precon)                                # :265-270
+            solve = getattr(cg_opt, "solve", None)
+            if solve is not None and self.reuse_cg_state:
+                v, cg_stats, state = solve(op, err, v_vec, precon)                      # :265-270
+            else:
+                v, cg_stats = cg_opt(op, err, v_vec, precon)
             v_vec.data.copy_(v)                                                         # :274
         v = v.reshape(-1, 1).contiguous()
-        Kv = op @ v                                                                     # :280
         r = torch.empty_like(v)
         scal = eng.empty(1)
-        eng.quad_terms(n, err, Kv, v, r, scal)                                          # :281, :283
-        z, eb = precon(r)                                                               # :282
+        if state is None:
+            Kv = op @ v                                                                 # :280
+            eng.quad_terms(n, err, Kv, v, r, scal)                                      # :281, :283
+            z, eb = precon(r)                                                           # :282
+        else:
+            # The reference recomputes cov @ v, r and P r after the solve because autograd needs them on the tape.
+            # The gradients here are closed-form, and the loop already holds all three for the returned v: its
+            # residual (recomputed as b - K v at the start and at every restart, r -= gamma K p in between), and
+            # z = P r, r^T z of its last preconditioner application (whose B^-1 A r the backward reads from
+            # `precon.w`).  K v = err - r saves one n^2 sweep and two passes over A per evaluation; the residual
+            # gap of the recurrence is O(eps k |K||v|), the size of the rounding error of one K v itself
+            # (tests/test_gpu_parity.py compares both routes; CGLB_RECOMPUTE_RESIDUAL=1 selects the reference's).
+            Kv = torch.sub(err, state.r.reshape(-1, 1))
+            eng.quad_terms(n, err, Kv, v, r, scal)
+            z, eb = state.z.reshape(-1, 1), state.rz
         lower = float(scal.item())
         eb = float(eb.item())
         upper = lower + 0.5 * eb                                                        # :284

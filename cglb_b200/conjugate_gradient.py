@@ -27,6 +27,16 @@ class ConjugateGradientStats:                      # reference conjugate_gradien
 
 
 @dataclass
+class ConjugateGradientState:
+    """What the loop holds when it stops: the residual of the returned v (from the recurrence r -= gamma A p, or
+    recomputed as b - A v at the start and at every restart), z = P r and r^T z of the LAST preconditioner
+    application, which was made with exactly this r.  Not part of the reference API (`solve` returns it)."""
+    r: Tensor
+    z: Tensor
+    rz: Tensor
+
+
+@dataclass
 class ConjugateGradient:
     """CG stops if: 0.5 * r^T Q^-1 r < max_error || i > max_cg_iter   (reference :31-39)"""
 
@@ -37,6 +47,13 @@ class ConjugateGradient:
     def __call__(self, A: Any, b: Tensor, v: Tensor, precond: Preconditioner) -> Tuple[Tensor, ConjugateGradientStats]:
         """:param A: operator supporting `A @ x` for x of shape [N, 1]  (reference :41-86)
         :param b: [N, 1] right-hand side;  :param v: [N, 1] warm start;  :param precond: r -> (z, r^T z)"""
+        v, stats, _ = self.solve(A, b, v, precond)
+        return v, stats
+
+    def solve(self, A: Any, b: Tensor, v: Tensor, precond: Preconditioner
+              ) -> Tuple[Tensor, ConjugateGradientStats, ConjugateGradientState]:
+        """`__call__` plus the final loop state, so that a caller that needs b - A v and P (b - A v) afterwards
+        (models.py:280-282) does not have to pay another n^2 sweep for them."""
         if not b.is_cuda:
             raise CglbError("ConjugateGradient needs CUDA tensors (cglb_b200 has no CPU fallback)")
         eng = get_engine(b.device)
@@ -67,7 +84,7 @@ class ConjugateGradient:
             rz_host = float(rz.item())                                # the loop test is evaluated on the host, as in :65
             i += 1
         stats = ConjugateGradientStats(i, torch.tensor(0.5 * rz_host, dtype=b.dtype))   # :83
-        return v, stats
+        return v, stats, ConjugateGradientState(r=r, z=z, rz=rz)
 
 
 @dataclass

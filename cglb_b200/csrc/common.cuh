@@ -144,7 +144,8 @@ __device__ __forceinline__ double fast_sqrt(double q) {
 //             coefficient (Chebyshev), 7 FP64 slots, max rel. error 9.4e-17 + rounding    (the sweeps;
 //             checked in 50-digit arithmetic by tests/test_kernel_arithmetic.py)
 // ln2/2^TB is a single double: its representation error (3.3e-17 relative) adds s * 3.3e-17 to the relative error of
-// e^-s (1e-15 at s = 30), the dominant term in practice.
+// e^-s (1e-15 at s = 30) -- next to the s * 1.1e-16 .. 2.2e-16 that the rounding of s itself costs any fp64
+// evaluation (the whole map in emulated fp64 against 50-digit arithmetic: tests/test_kernel_arithmetic.py).
 // The caller clamps s to [0, 693] (kappa() does it on the squared distance with two integer min/max), so
 // e^-s >= 2^-1000 and the exponent-field add cannot wrap: no separate exponent clamp.
 // Instruction diet (profiles/README_r02.md): every non-FP64 instruction costs the FP64 pipe ~1 issue cycle in

@@ -422,6 +422,42 @@ def test_warm_start_sequence_matches_oracle_iteration_counts():
     assert float(model.v_vec.abs().max()) > 0
 
 
+@pytest.mark.parametrize("M,noise,max_error,expect_restart", [(24, 0.3, 1.0, False), (64, 0.02, 1e-3, True)])
+def test_cg_state_reuse_matches_the_recomputed_route(M, noise, max_error, expect_restart):
+    """models.py:280-282 recomputes K v, r and P r after the solve; the device path takes them from the final CG state
+    (bound.py: reuse_cg_state, one n^2 sweep less per evaluation).  Both routes at the SAME v: the solve with reuse,
+    then the reference's cached-v route (models.py:263-264), which recomputes all three; then the solve again with
+    reuse switched off.  k + 1 + floor(k/40) against k + 2 + floor(k/40) sweeps, bound and gradients equal far inside
+    the tolerance (the CPU side of the claim: tests/test_cg_residual_reuse.py)."""
+    n, d = 1400, 5
+    x, y, z = o.synthetic_problem(n, d, M, seed=21)
+    model = make_model("matern32", x.numpy(), y.numpy(), z.numpy(), noise, 1.1, 1.3, 0.02)
+    data = (model.train_inputs[0], model.train_targets)
+    params = list(model.parameters())
+    lb = cb.LowerBoundCG(model, cg_opt=cb.ConjugateGradient(max_error=max_error))
+    assert lb.evaluator(data).reuse_cg_state
+    loss = -lb(data)
+    grads = [g_.cpu().numpy() for g_ in torch.autograd.grad(loss, params)]
+    k = int(model.cg_stats.steps)
+    assert (k >= 40) == expect_restart and k < 100
+    assert lb.last_output.matvecs == k + 1 + k // 40
+    # the recomputed route at the same v
+    lb_c = cb.LowerBoundCG(model, use_cache=True, cached_v_vec_initial=True)
+    loss_c = -lb_c(data)
+    grads_c = [g_.cpu().numpy() for g_ in torch.autograd.grad(loss_c, params)]
+    assert lb_c.last_output.matvecs == 1
+    assert abs(float(loss) - float(loss_c)) <= 1e-11 * abs(float(loss_c))
+    for nm, a, b in zip(GRAD_NAMES, grads, grads_c):
+        assert np.abs(a - b).max() <= 1e-8 * np.abs(b).max() + 1e-10, nm
+    # the reference's count with reuse switched off (what CGLB_RECOMPUTE_RESIDUAL=1 selects)
+    model.v_vec.data.zero_()
+    lb.evaluator(data).reuse_cg_state = False
+    loss_r = -lb(data)
+    k_r = int(model.cg_stats.steps)
+    assert abs(k_r - k) <= 1 and lb.last_output.matvecs == k_r + 2 + k_r // 40
+    assert abs(float(loss) - float(loss_r)) <= BOUND_TOL * abs(float(loss_r))
+
+
 @pytest.mark.parametrize("name", ["road_like_trained", "house_like_warmstart", "snelson_like_init"])
 def test_predict_matches_reference_golden(name):
     g = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
