@@ -25,7 +25,7 @@ NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nv
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr"]
-PLAIN_UNITS = ["context.cu", "kmv_api.cu", "dense.cu", "vecops.cu", "knm.cu", "widek.cu", "dsweep.cu"]
+PLAIN_UNITS = ["context.cu", "kmv_api.cu", "dense.cu", "vecops.cu", "widek.cu", "dsweep.cu"]
 ALL_DIMS = list(range(1, 33))
 
 

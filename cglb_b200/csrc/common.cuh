@@ -148,7 +148,7 @@ __device__ __forceinline__ double fast_sqrt(double q) {
 // evaluation (the whole map in emulated fp64 against 50-digit arithmetic: tests/test_kernel_arithmetic.py).
 // The caller clamps s to [0, 693] (kappa() does it on the squared distance with two integer min/max), so
 // e^-s >= 2^-1000 and the exponent-field add cannot wrap: no separate exponent clamp.
-// Instruction diet (profiles/README_r02.md): every non-FP64 instruction costs the FP64 pipe ~1 issue cycle in
+// Instruction diet (profiles/dsweep_ncu_r01.md, profiles/fp64_issue_model_r01.txt): every non-FP64 instruction costs the FP64 pipe ~1 issue cycle in
 // these kernels, and a DFMA reading three distinct vector registers issues at 2/3 rate (tools/fp64_issue_model.cu);
 // hence e^r = T * (1 + r p) as DFMA(2 regs + imm) + DMUL and the exponent insert as LOP3 + IMAD.
 constexpr int kExpTabSmall = 64;

@@ -1,7 +1,7 @@
 // K1 for d <= 32 with the distance contraction on DMMA.8x8x4 ("dsweep").
 //
 // Why: on sm_100a every non-FP64 instruction of these sweeps costs the shared FP64/DMMA pipe about one issue
-// cycle (measured: profiles/README_r02.md, tools/fp64_issue_model.cu, tools/fp64_mix_model.cu).  In the
+// cycle (measured: profiles/dsweep_ncu_r01.md, profiles/fp64_issue_model_r01.txt, tools/fp64_issue_model.cu, tools/fp64_mix_model.cu).  In the
 // register-resident sweep (kmv_impl.cuh) a Matern32 pair at d = 11 is 27 FP64 instructions + ~15 integer / LDS /
 // MUFU instructions.  DMMA.8x8x4 performs the 256 FMAs of 8 warp-wide DFMAs in ONE instruction (same pipe
 // time), so moving the d + 1 distance FMAs onto it removes ~11 instructions per pair and most of the LDS
@@ -78,7 +78,7 @@ struct DCursor {
 
 // WARPS warps x MT m-tiles (8 rows each) per warp; lane 0 of warp 0 also drives the TMA ring, as in the
 // register-resident sweep (a dedicated producer warp and 12 / 16-warp shapes were measured and are slower,
-// profiles/README_r02.md)
+// profiles/dsweep_ncu_r01.md, profiles/fp64_issue_model_r01.txt)
 template <int KIND, int DP, int WARPS, int MT>
 __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepArgs args, const long n_chunks) {
     constexpr int KS = (DP + 3) / 4;    // k-steps; slots DP .. 4 KS - 1 belong to the next packed row (A carries 0 there)
