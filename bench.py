@@ -25,6 +25,7 @@ import sys
 import threading
 import time
 
+T_PROCESS_START = time.time()
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -178,6 +179,77 @@ def run_reference(args, rank):
 # ================================================================================================
 # own arm
 # ================================================================================================
+class Budget:
+    """Wall-clock budget of the whole process (the driver kills the command at a fixed limit: 870 s per N in its
+    scaling run).  A step of the n = 2M config costs 70-90 s on one B200, so `--steps 20 --warmup 5` cannot fit on
+    1 or 2 GPUs on any FP64 roofline: the loops below run as many of the requested steps as fit and the line says
+    how many (`steps`, `warmup` = executed; `config.steps_requested`, `config.warmup_requested`,
+    `config.truncated_by_budget`)."""
+    SAFETY = 1.25          # the CG iteration count cycles with the lengthscale perturbation: steps differ by +-12 %
+
+    def __init__(self, seconds, reserve):
+        self.seconds, self.reserve = float(seconds), float(reserve)
+
+    def left(self):
+        return self.seconds - (time.time() - T_PROCESS_START) - self.reserve
+
+    def fits(self, step_seconds, steps=1):
+        return self.left() >= self.SAFETY * step_seconds * steps
+
+
+def multi_gpu_parity(cb, dev, rank, world, shard, kind, d, th):
+    """N > 1 only: the same bound + gradients (a) row-sharded over all ranks and (b) on rank 0 alone, on a seeded
+    sub-sample of the workload, at a fixed v (tolerance 1e-9) and along a warm-started CG trajectory (iteration
+    counts equal, bound 1e-7) -- so that the scaling record itself carries a multi-GPU parity check."""
+    import torch.distributed as dist
+    n_s, m_s = 24000, 256
+    x, y, z = synthetic(n_s, d, m_s, seed=11)
+    g = torch.Generator().manual_seed(12)
+    v_fixed = 0.05 * torch.randn(n_s, 1, generator=g, dtype=torch.float64)
+
+    def build(sh):
+        lik = cb.GaussianLikelihood(noise_constraint=cb.GreaterThan(1e-6)).double()
+        lik.noise = 0.1 if th["noise"] > 0.1 else th["noise"]
+        base = (cb.MaternKernel(nu=1.5, ard_num_dims=d) if kind == "matern32" else cb.RBFKernel(ard_num_dims=d)).double()
+        base.lengthscale = torch.full((d,), th["ls"](d), dtype=torch.float64)
+        scale = cb.ScaleKernel(base).double()
+        scale.outputscale = th["variance"]
+        model = cb.CGLB((x.to(dev), y.to(dev)), lik, cb.InducingPointKernel(scale, z, likelihood=lik)).double().to(dev)
+        return model, sh
+
+    def run(sh, cached):
+        model, _ = build(sh)
+        data = (model.train_inputs[0], model.train_targets)
+        if cached:
+            model.v_vec.data.copy_(v_fixed.to(dev))
+            lb = cb.LowerBoundCG(model, use_cache=True, cached_v_vec_initial=True, shard=sh)
+        else:
+            lb = cb.LowerBoundCG(model, shard=sh)
+        loss = -lb(data)
+        grads = torch.autograd.grad(loss, list(model.parameters()))
+        flat = torch.cat([loss.detach().reshape(1)] + [g_.detach().reshape(-1) for g_ in grads]).double().cpu()
+        steps = int(model.cg_stats.steps) if not cached else 0
+        return flat, steps
+
+    out = {}
+    for name, cached in (("fixed_v", True), ("cg_trajectory", False)):
+        sharded, steps_sh = run(shard, cached)
+        dist.barrier()
+        if rank == 0:
+            single, steps_1 = run(cb.Shard(0, 1, None), cached)
+            rel_loss = float(abs(sharded[0] - single[0]) / abs(single[0]))
+            rel_grad = float((sharded[1:] - single[1:]).abs().max() / single[1:].abs().max())
+            out[name] = {"rel_loss": rel_loss, "rel_grad_max": rel_grad, "cg_steps_sharded": steps_sh, "cg_steps_single": steps_1}
+        dist.barrier()
+    if rank == 0:
+        out["n"], out["M"], out["ranks"] = n_s, m_s, world
+        ok = (out["fixed_v"]["rel_loss"] <= 1e-9 and out["fixed_v"]["rel_grad_max"] <= 1e-9
+              and out["cg_trajectory"]["rel_loss"] <= 1e-7
+              and abs(out["cg_trajectory"]["cg_steps_sharded"] - out["cg_trajectory"]["cg_steps_single"]) <= 1)
+        out["ok"] = bool(ok)
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     import cglb_b200 as cb
@@ -220,7 +292,6 @@ def run_b200(args, rank, world, local_rank):
     eval_func = cb.Scipy.eval_func(closure, params)             # the reference's bound+gradient call (a10)
     x0 = cb.Scipy.to_numpy(cb.Scipy.pack(params)).astype(np.float64)
     ls_slice = slice(x0.size - d, x0.size)                      # raw lengthscale is the last parameter
-    raw_ls0 = x0[ls_slice].copy()
     base_ls = th["ls"](d)
 
     def theta_vector(step_idx):
@@ -233,8 +304,11 @@ def run_b200(args, rank, world, local_rank):
     h2d_bytes = x_pin.numel() * x_pin.element_size() + y_pin.numel() * y_pin.element_size() + x0.size * 8
     d2h_bytes = (x0.size + 1) * 8
     stats = []
+    tmax = torch.zeros(2, dtype=torch.float64, device=dev)
 
     def one_step(step_idx, timed):
+        """One bound + gradient evaluation, barrier + synchronize on both sides, CUDA events on the launching
+        stream; returns (device-timed ms, end-to-end ms), each the MAX over ranks."""
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         if world > 1:
             dist.barrier()
@@ -248,7 +322,10 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
-        t_dev, t_e2e = ev[1].elapsed_time(ev[2]), ev[0].elapsed_time(ev[2])
+        tmax[0], tmax[1] = ev[1].elapsed_time(ev[2]), ev[0].elapsed_time(ev[2])
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)          # outside the timed region
+        t_dev, t_e2e = float(tmax[0]), float(tmax[1])
         if timed:
             out = lower_bound.last_output
             stats.append(dict(ms=t_dev, ms_e2e=t_e2e, cg=int(out.cg_stats.steps), matvecs=out.matvecs, loss=float(loss)))
@@ -258,109 +335,165 @@ def run_b200(args, rank, world, local_rank):
         if rank == 0:
             print(f"[bench] {msg}", file=sys.stderr, flush=True)
 
-    note(f"{desc}, theta={args.theta}, {world} GPU(s): {args.warmup} warm-up + {args.steps} timed steps")
+    def agree(flag):
+        """rank 0's decision for everybody (the budget clock differs by a few ms between ranks)"""
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
+        dist.broadcast(t, src=0)
+        return bool(t.item() > 0.5)
+
+    # reserve: cpu_baseline leg (N = 1) or the multi-GPU parity check (N > 1) + teardown
+    budget = Budget(args.max_seconds, reserve=(35.0 if world == 1 and not args.no_cpu_baseline else 20.0))
+    min_timed = min(args.steps, 3)
+    note(f"{desc}, theta={args.theta}, {world} GPU(s): up to {args.warmup} warm-up + {args.steps} timed steps within "
+         f"{args.max_seconds:.0f} s of wall clock ({time.time() - T_PROCESS_START:.0f} s spent on start-up and data)")
+    # ---- warm-up: the cold step + at least one warm one; more (up to --warmup) only while the timed steps still fit
+    recent, warm_done = [], 0
     for i in range(args.warmup):
+        if warm_done >= min(2, args.warmup) and not agree(budget.fits(max(recent[-3:]), min_timed + 1)):
+            note(f"warm-up stopped after {warm_done} of {args.warmup} steps: the remaining budget ({budget.left():.0f} s) is kept "
+                 f"for {min_timed} timed steps of ~{max(recent[-3:]):.0f} s")
+            break
         td, _ = one_step(i, False)
-        note(f"warm-up step {i + 1}/{args.warmup}: {td / 1e3:.2f} s")
+        recent.append(td / 1e3)
+        warm_done += 1
+        note(f"warm-up step {warm_done}/{args.warmup}: {td / 1e3:.2f} s")
+
     eng.enable_timing(True)
     launches0 = eng.launch_count
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    times = []
-    for i in range(args.steps):
-        times.append(one_step(args.warmup + i, True))
-        note(f"timed step {i + 1}/{args.steps}: {times[-1][0] / 1e3:.2f} s, CG iterations {stats[-1]['cg']}")
-    clocks = sampler.stop() if sampler else None
-    launches = eng.launch_count - launches0
-    ksum = eng.timing_summary()
-    eng.enable_timing(False)
 
-    t_dev = torch.tensor([sum(t[0] for t in times), sum(t[1] for t in times)], dtype=torch.float64, device=dev)
-    lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
-    kt = torch.tensor([ksum.get("kmv_sym", (0, 0.0))[1], ksum.get("kmv_bwd_sym", (0, 0.0))[1],
-                       ksum.get("precond_project", (0, 0.0))[1] + ksum.get("precond_finish", (0, 0.0))[1],
-                       ksum.get("trsm", (0, 0.0))[1] + ksum.get("syrk", (0, 0.0))[1] + ksum.get("gemm", (0, 0.0))[1]],
-                      dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)             # max over ranks
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    ms_step = float(t_dev[0]) / args.steps
-    ms_e2e = float(t_dev[1]) / args.steps
-    n_kmv = ksum.get("kmv_sym", (0, 0.0))[0]
     fpp = algorithmic_flops_per_pair(kind, d)
     peaks = load_json(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")) or {}
     measured = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
     fp64_peak = float(peaks.get("fp64_peak_tflops_used_as_denominator", 37.1))
     hbm_peak = float(measured.get("hbm_gbs", 6650.0))
-    # dominant kernel: the symmetric K v sweep.  Algorithmic FLOPs per launch on this rank = (3d+7) n^2 / world.
-    kmv_ms = float(kt[0]) / max(n_kmv, 1)
-    achieved = fpp * float(n) * n / world / (kmv_ms * 1e-3) / 1e12 if n_kmv else None
-    ncu = load_json(os.path.join(ROOT, "profiles", "kmv_ncu_summary.json")) or {}
-    # DRAM bytes per launch (ncu, per rank): every rank streams the whole packed input array once, whatever its share of
-    # the work items, so the single-GPU figure holds for every N
-    traffic = ncu.get(f"{args.workload}", {}).get("dram_bytes_per_launch")
+    ncu_all = load_json(os.path.join(ROOT, "profiles", "kmv_ncu_summary.json")) or {}
     variant = eng.kmv_sym_variant(d, n, world)
     diag_block = {0: 1024.0, 1: 256.0, 2: 128.0}[variant]      # rows of the diagonal blocks, evaluated as full squares
     eval_frac = 0.5 + 0.5 * min(1.0, diag_block / n)
-    n_pre = ksum.get("precond_project", (0, 0.0))[0]
-    pre_bytes = 2.0 * M * (n / world) * 8 + 4.0 * (n / world) * 8
-    pre_ms = float(kt[2]) / max(n_pre, 1)
-    line = {
-        "metric": "cglb_bound_grad_step_time", "value": ms_step * 1e-3, "unit": "s/step", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64" if args.float_type == "fp64" else "f32 kernel pairs, f64 accumulation and linear algebra",
-        "data": "synthetic",
-        "config": {"workload": (desc if not args.n else f"{desc} (n overridden to {n})") +
-                               ("" if args.float_type == "fp64" else " -- run in the fp32 mode of the API, NOT the fp64 metric of BASELINE.json"),
-                   "theta": args.theta, "kernel": kind, "n": n, "d": d, "M": M, "parallelism": f"row-sharded x{world}",
-                   "cg": "reference defaults (max_error=1, max_cg_iter=100, restart=40), warm start carried across steps, "
-                         "lengthscales perturbed by (1, 1.01, 0.99) per step; K v, r and P r after the solve come from the final "
-                         "CG state (k + 1 + floor(k/40) sweeps per step; the reference recomputes them for its autograd tape: "
-                         "k + 2 + floor(k/40); CGLB_RECOMPUTE_RESIDUAL=1 selects that)",
-                   "cg_steps": [s["cg"] for s in stats], "kv_sweeps_per_step": [s["matvecs"] for s in stats],
-                   "loss": [s["loss"] for s in stats],
-                   "l2": "inputs larger than L2 (X packed %.0f MB, A %.1f GB per rank)" % (n * (d + 2) * 8 / 1e6, M * n / world * 8 / 1e9)},
-        "kv_gpairs_per_s": (float(n) * n / (kmv_ms * 1e-3) / 1e9) if n_kmv else None,
-        "e2e": {"value": ms_e2e * 1e-3, "unit": "s/step", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-        "gpu_launches": int(lt.item()),
-        "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "K1 symmetric matrix-free K*v: " + eng.KMV_VARIANTS[variant],
-                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if achieved else None,
-                     "traffic": traffic,
-                     "note": "algorithmic-FLOP fraction: (3d+7) n^2 FLOP per K*v (SURVEY.md 8d) / CUDA-event time per launch; "
-                             "FP64 has no tcgen05 path, the denominator is the measured DMMA.8x8x4 rate "
-                             "(profiles/fp64_peaks_r01.json, 'of measured'); the symmetric sweep evaluates each unordered pair once, so `achieved` "
-                             "(nominal n^2 pairs of the reference's K*v) can exceed the peak; `achieved_evaluated` counts only the pairs "
-                             "actually evaluated (n^2/2 + the diagonal blocks)",
-                     "achieved_evaluated": (achieved * eval_frac) if achieved else None,
-                     "frac_evaluated": (achieved * eval_frac / fp64_peak) if achieved else None,
-                     "fp64_pipe_utilisation_ncu": (ncu.get("fp64_pipe_active_pct_by_variant") or {}).get(str(variant), ncu.get("fp64_pipe_active_pct")),
-                     "launches": n_kmv, "ms_per_launch": kmv_ms,
-                     "share_of_step": float(kt[0]) / float(t_dev[0]) if float(t_dev[0]) else None},
-        "roofline_other": {
-            "precond_gemv_pair": {"bound": "hbm", "achieved": (pre_bytes / (pre_ms * 1e-3) / 1e9) if n_pre else None,
-                                  "peak": hbm_peak, "unit": "GB/s",
-                                  "frac": (pre_bytes / (pre_ms * 1e-3) / 1e9 / hbm_peak) if n_pre else None,
-                                  "share_of_step": float(kt[2]) / float(t_dev[0]) if float(t_dev[0]) else None,
-                                  "note": "two read-only streaming passes over A per apply; MEASURED_PEAKS.json's hbm_gbs is a "
-                                          "read+write copy, which a pure read stream can exceed (frac > 1 at the largest sizes)"},
-            "backward_sweep": {"share_of_step": float(kt[1]) / float(t_dev[0]) if float(t_dev[0]) else None,
-                               "ms_per_launch": float(kt[1]) / max(ksum.get("kmv_bwd_sym", (1, 0))[0], 1)},
-            "dense_trsm_syrk_gemm": {"share_of_step": float(kt[3]) / float(t_dev[0]) if float(t_dev[0]) else None}},
-    }
-    if args.float_type == "fp32" and d <= 32:
-        # exploration: the sweep that ran is f32_sweep_kernel (FP32 FMA + MUFU pipes); the FP64 roofline does not apply
-        line["roofline"].update({"kernel": "K1 symmetric matrix-free K*v: f32_sweep_kernel (FP32 kernel pairs, FP64 accumulation)",
-                                 "frac": None, "achieved_evaluated": None, "frac_evaluated": None, "fp64_pipe_utilisation_ncu": None,
-                                 "note": "fp32 mode of the API: 2 MUFU + ~17 FP32 + ~3 other instructions per pair, issue-bound; "
-                                         "`achieved` is still the nominal (3d+7) n^2 figure, not comparable with the FP64 peak"})
+
+    def make_line(partial, clocks=None, launches=None, ksum=None, kt=None, extra_config=None):
+        steps_done = len(stats)
+        ms_step = sum(s["ms"] for s in stats) / steps_done
+        ms_e2e = sum(s["ms_e2e"] for s in stats) / steps_done
+        total_ms = ms_step * steps_done
+        n_kmv = ksum.get("kmv_sym", (0, 0.0))[0]
+        # dominant kernel: the symmetric K v sweep.  One launch on this rank EVALUATES (n^2/2 + diagonal blocks) / world
+        # kernel pairs; algorithmic FLOPs per evaluated pair as in SURVEY.md 8d (3d+7 Matern32, 3d+4 RBF, 2d+10 wide).
+        kmv_ms = float(kt[0]) / max(n_kmv, 1)
+        nominal = fpp * float(n) * n / world / (kmv_ms * 1e-3) / 1e12 if n_kmv else None
+        achieved = nominal * eval_frac if n_kmv else None
+        ncu = ncu_all.get(args.workload, {}) if world == 1 and not args.n else {}
+        n_pre = ksum.get("precond_project", (0, 0.0))[0]
+        pre_bytes = 2.0 * M * (n / world) * 8 + 4.0 * (n / world) * 8
+        pre_ms = float(kt[2]) / max(n_pre, 1)
+        cfg = {"workload": (desc if not args.n else f"{desc} (n overridden to {n})") +
+                           ("" if args.float_type == "fp64" else " -- run in the fp32 mode of the API, NOT the fp64 metric of BASELINE.json"),
+               "theta": args.theta, "kernel": kind, "n": n, "d": d, "M": M, "parallelism": f"row-sharded x{world}",
+               "steps_requested": args.steps, "warmup_requested": args.warmup,
+               "truncated_by_budget": bool(steps_done < args.steps or warm_done < args.warmup),
+               "max_seconds": args.max_seconds,
+               "cg": "reference defaults (max_error=1, max_cg_iter=100, restart=40), warm start carried across steps, "
+                     "lengthscales perturbed by (1, 1.01, 0.99) per step; K v, r and P r after the solve come from the final "
+                     "CG state (k + 1 + floor(k/40) sweeps per step; the reference recomputes them for its autograd tape: "
+                     "k + 2 + floor(k/40); CGLB_RECOMPUTE_RESIDUAL=1 selects that)",
+               "cg_steps": [s["cg"] for s in stats], "kv_sweeps_per_step": [s["matvecs"] for s in stats],
+               "step_seconds": [round(s["ms"] * 1e-3, 4) for s in stats],
+               "loss": [s["loss"] for s in stats],
+               "l2": "inputs larger than L2 (X packed %.0f MB, A %.1f GB per rank)" % (n * (d + 2) * 8 / 1e6, M * n / world * 8 / 1e9)}
+        if extra_config:
+            cfg.update(extra_config)
+        line = {
+            "metric": "cglb_bound_grad_step_time", "value": ms_step * 1e-3, "unit": "s/step", "n_gpus": world,
+            "steps": steps_done, "warmup": warm_done, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64" if args.float_type == "fp64" else "f32 kernel pairs, f64 accumulation and linear algebra",
+            "data": "synthetic", "config": cfg,
+            "kv_gpairs_per_s": (float(n) * n / (kmv_ms * 1e-3) / 1e9) if n_kmv else None,
+            "e2e": {"value": ms_e2e * 1e-3, "unit": "s/step", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "K1 symmetric matrix-free K*v: " + eng.KMV_VARIANTS[variant],
+                         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if achieved else None,
+                         "peak_source": "profiles/fp64_peaks_r01.json: DMMA.8x8x4 loop measured on this pool's B200 (MEASURED_PEAKS.json "
+                                        "has no FP64 figure); FP64 has no tcgen05 path",
+                         "traffic": ncu.get("dram_bytes_per_launch"),
+                         "traffic_source": ncu.get("source") if ncu.get("dram_bytes_per_launch") else None,
+                         "note": "achieved = algorithmic FLOPs of the kernel pairs one launch EVALUATES (the symmetric sweep visits each "
+                                 "unordered pair once: n^2/2 + the diagonal blocks, SURVEY.md 8d FLOPs per pair) / CUDA-event time per launch, "
+                                 "measured live in this run; achieved_nominal_n2 counts the n^2 ordered pairs of the reference's K*v instead",
+                         "achieved_nominal_n2": nominal,
+                         "pairs_evaluated_fraction_of_n2": eval_frac,
+                         "launches": n_kmv, "ms_per_launch": kmv_ms,
+                         "share_of_step": float(kt[0]) / total_ms if total_ms else None},
+            "roofline_other": {
+                "precond_gemv_pair": {"bound": "hbm", "achieved": (pre_bytes / (pre_ms * 1e-3) / 1e9) if n_pre else None,
+                                      "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": (pre_bytes / (pre_ms * 1e-3) / 1e9 / hbm_peak) if n_pre else None,
+                                      "share_of_step": float(kt[2]) / total_ms if total_ms else None,
+                                      "note": "two read-only streaming passes over A per apply; MEASURED_PEAKS.json's hbm_gbs is a "
+                                              "read+write copy, which a pure read stream can exceed (frac > 1 at the largest sizes)"},
+                "backward_sweep": {"share_of_step": float(kt[1]) / total_ms if total_ms else None,
+                                   "ms_per_launch": float(kt[1]) / max(ksum.get("kmv_bwd_sym", (1, 0))[0], 1)},
+                "dense_trsm_syrk_gemm": {"share_of_step": float(kt[3]) / total_ms if total_ms else None}},
+        }
+        if partial:
+            line["partial"] = True
+        if args.float_type == "fp32" and d <= 32:
+            # exploration: the sweep that ran is f32_sweep_kernel (FP32 FMA + MUFU pipes); the FP64 roofline does not apply
+            line["roofline"].update({"kernel": "K1 symmetric matrix-free K*v: f32_sweep_kernel (FP32 kernel pairs, FP64 accumulation)",
+                                     "frac": None,
+                                     "note": "fp32 mode of the API: 2 MUFU + ~17 FP32 + ~3 other instructions per pair, issue-bound; "
+                                             "`achieved` is still the FP64 convention's figure, not comparable with the FP64 peak"})
+        return line
+
+    def kernel_times():
+        ksum = eng.timing_summary()
+        kt = [ksum.get("kmv_sym", (0, 0.0))[1], ksum.get("kmv_bwd_sym", (0, 0.0))[1],
+              ksum.get("precond_project", (0, 0.0))[1] + ksum.get("precond_finish", (0, 0.0))[1],
+              ksum.get("trsm", (0, 0.0))[1] + ksum.get("syrk", (0, 0.0))[1] + ksum.get("gemm", (0, 0.0))[1]]
+        return ksum, kt
+
+    # ---- timed steps: EXACTLY --steps of them when they fit; otherwise as many as fit, in whole periods of the
+    # 3-step lengthscale cycle (so that a truncated run and a full one average over the same mix of CG iteration counts)
+    truncated = False
+    for i in range(args.steps):
+        if i >= 1 and not agree(budget.fits(max(recent[-3:]))):
+            truncated = True
+            break
+        td, _ = one_step(warm_done + i, True)
+        recent.append(td / 1e3)
+        note(f"timed step {i + 1}/{args.steps}: {td / 1e3:.2f} s, CG iterations {stats[-1]['cg']}")
+        if rank == 0 and td > 5e3 and i + 1 < args.steps:
+            # long steps (n = 2M on 1-2 GPUs): leave a parsable cumulative line behind after every step, in case the
+            # process is killed at an outer limit; the complete line comes last
+            ksum_p, kt_p = kernel_times()
+            print(json.dumps(make_line(True, launches=eng.launch_count - launches0, ksum=ksum_p, kt=kt_p)), flush=True)
+    if truncated and len(stats) > 3 and len(stats) % 3:
+        del stats[len(stats) - len(stats) % 3:]
+        note(f"budget reached: reporting the first {len(stats)} timed steps (whole periods of the 3-step lengthscale cycle)")
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count - launches0
+    ksum, kt_list = kernel_times()
+    eng.enable_timing(False)
+
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    kt = torch.tensor(kt_list, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    extra = {}
+    if world > 1 and not args.no_parity_check:
+        par = multi_gpu_parity(cb, dev, rank, world, shard, kind, d, th)
+        extra["multi_gpu_parity"] = par
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = make_line(False, clocks=clocks, launches=int(lt.item()), ksum=ksum, kt=kt.tolist(), extra_config=extra)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(kind, n, d, M, th, stats)
     print(json.dumps(line), flush=True)
@@ -373,6 +506,8 @@ def run_b200(args, rank, world, local_rank):
         pass
     if world > 1:
         dist.destroy_process_group()
+    if extra.get("multi_gpu_parity") and not extra["multi_gpu_parity"].get("ok", False):
+        raise SystemExit(f"bench.py: multi-GPU parity check failed: {extra['multi_gpu_parity']}")
 
 
 def cpu_baseline(kind, n, d, M, th, stats):
@@ -404,8 +539,12 @@ def cpu_baseline(kind, n, d, M, th, stats):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1)      # n = 2M on one GPU is ~90 s per step (15-17 CG iterations)
+    ap.add_argument("--steps", type=int, default=3)      # n = 2M on one GPU is 70-90 s per step (15-19 CG iterations)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--max-seconds", type=float, default=float(os.environ.get("CGLB_BENCH_MAX_SECONDS", 700.0)),
+                    help="wall-clock budget of the whole process (start-up, data, warm-up, timed steps, CPU baseline): the loops run "
+                         "as many of the requested steps as fit and the line reports how many")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the sharded-vs-single-rank parity check")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--theta", default="init", choices=sorted(THETAS))

@@ -33,3 +33,30 @@ def test_own_arm_has_no_cpu_fallback():
         return
     r = _run("--workload", "snelson1d", "--steps", "1", "--warmup", "1")
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_budget_projection():
+    """The wall-clock budget that keeps `--steps 20 --warmup 5` inside the driver's limits (round 1 was killed)."""
+    sys.path.insert(0, ROOT)
+    import time
+    import bench
+    b = bench.Budget(seconds=(time.time() - bench.T_PROCESS_START) + 400.0, reserve=35.0)
+    assert 360.0 < b.left() <= 365.0
+    assert b.fits(80.0, 3)              # 3 x 80 s x 1.25 = 300 s
+    assert not b.fits(80.0, 4)          # 400 s
+    assert not b.fits(300.0)
+
+
+def test_committed_bench_lines_respect_the_roofline_convention():
+    """roofline.frac counts the pairs a launch EVALUATES (the nominal n^2 figure read as 104-150 % of peak)."""
+    import glob
+    lines = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_*_r02*.json")))
+    for path in lines:
+        with open(path) as f:
+            j = json.load(f)
+        if j.get("impl") == "reference":
+            continue
+        frac = j["roofline"]["frac"]
+        assert frac is None or 0.0 < frac <= 1.0, (path, frac)
+        assert "achieved_nominal_n2" in j["roofline"]
+        assert j["steps"] >= 1 and j["config"]["steps_requested"] >= j["steps"]
