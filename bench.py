@@ -193,8 +193,16 @@ class Budget:
     def left(self):
         return self.seconds - (time.time() - T_PROCESS_START) - self.reserve
 
-    def fits(self, step_seconds, steps=1):
-        return self.left() >= self.SAFETY * step_seconds * steps
+    def fits(self, step_seconds, steps=1, safety=None):
+        return self.left() >= (self.SAFETY if safety is None else safety) * step_seconds * steps
+
+    @staticmethod
+    def estimate(step_times):
+        """(seconds per step, safety factor) from the steps run so far.  The first step starts CG from v = 0 and takes
+        2-3x the iterations of a warm-started one: it is left out as soon as a warm step exists.  With a whole period of
+        the 3-step lengthscale cycle observed, the maximum IS the longest step."""
+        warm = step_times[1:] if len(step_times) > 1 else step_times
+        return max(warm[-3:]), (1.05 if len(warm) >= 3 else Budget.SAFETY)
 
 
 def multi_gpu_parity(cb, dev, rank, world, shard, kind, d, th):
@@ -351,10 +359,12 @@ def run_b200(args, rank, world, local_rank):
     # ---- warm-up: the cold step + at least one warm one; more (up to --warmup) only while the timed steps still fit
     recent, warm_done = [], 0
     for i in range(args.warmup):
-        if warm_done >= min(2, args.warmup) and not agree(budget.fits(max(recent[-3:]), min_timed + 1)):
-            note(f"warm-up stopped after {warm_done} of {args.warmup} steps: the remaining budget ({budget.left():.0f} s) is kept "
-                 f"for {min_timed} timed steps of ~{max(recent[-3:]):.0f} s")
-            break
+        if warm_done >= min(2, args.warmup):
+            est, safety = Budget.estimate(recent)
+            if not agree(budget.fits(est, min_timed + 1, safety)):
+                note(f"warm-up stopped after {warm_done} of {args.warmup} steps: the remaining budget ({budget.left():.0f} s) is kept "
+                     f"for {min_timed} timed steps of ~{est:.0f} s")
+                break
         td, _ = one_step(i, False)
         recent.append(td / 1e3)
         warm_done += 1
@@ -371,7 +381,9 @@ def run_b200(args, rank, world, local_rank):
     measured = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
     fp64_peak = float(peaks.get("fp64_peak_tflops_used_as_denominator", 37.1))
     hbm_peak = float(measured.get("hbm_gbs", 6650.0))
-    ncu_all = load_json(os.path.join(ROOT, "profiles", "kmv_ncu_summary.json")) or {}
+    # dram__bytes_read + write of the dominant kernel per launch, from ncu --set full captures AT THE WORKLOAD'S OWN SHAPE
+    # (profiles/kmv_ncu_r02.json names the report each number comes from); null where no such capture exists
+    ncu_all = load_json(os.path.join(ROOT, "profiles", "kmv_ncu_r02.json")) or {}
     variant = eng.kmv_sym_variant(d, n, world)
     diag_block = {0: 1024.0, 1: 256.0, 2: 128.0}[variant]      # rows of the diagonal blocks, evaluated as full squares
     eval_frac = 0.5 + 0.5 * min(1.0, diag_block / n)
@@ -460,24 +472,30 @@ def run_b200(args, rank, world, local_rank):
     # ---- timed steps: EXACTLY --steps of them when they fit; otherwise as many as fit, in whole periods of the
     # 3-step lengthscale cycle (so that a truncated run and a full one average over the same mix of CG iteration counts)
     truncated = False
+    per_step = []            # cumulative (launch count, kernel-time summary) after every timed step
     for i in range(args.steps):
-        if i >= 1 and not agree(budget.fits(max(recent[-3:]))):
-            truncated = True
-            break
+        if i >= 1:
+            est, safety = Budget.estimate(recent)
+            # past the first period, a new period of the cycle is only started if all of it fits (a partial one is dropped)
+            need = min(3, args.steps - i) if (i >= 3 and i % 3 == 0) else 1
+            if not agree(budget.fits(est, need, safety)):
+                truncated = True
+                break
         td, _ = one_step(warm_done + i, True)
         recent.append(td / 1e3)
         note(f"timed step {i + 1}/{args.steps}: {td / 1e3:.2f} s, CG iterations {stats[-1]['cg']}")
+        per_step.append((eng.launch_count - launches0, *kernel_times()))
         if rank == 0 and td > 5e3 and i + 1 < args.steps:
             # long steps (n = 2M on 1-2 GPUs): leave a parsable cumulative line behind after every step, in case the
             # process is killed at an outer limit; the complete line comes last
-            ksum_p, kt_p = kernel_times()
-            print(json.dumps(make_line(True, launches=eng.launch_count - launches0, ksum=ksum_p, kt=kt_p)), flush=True)
+            print(json.dumps(make_line(True, launches=per_step[-1][0], ksum=per_step[-1][1], kt=per_step[-1][2])), flush=True)
     if truncated and len(stats) > 3 and len(stats) % 3:
-        del stats[len(stats) - len(stats) % 3:]
+        keep = len(stats) - len(stats) % 3
+        del stats[keep:]
+        del per_step[keep:]
         note(f"budget reached: reporting the first {len(stats)} timed steps (whole periods of the 3-step lengthscale cycle)")
     clocks = sampler.stop() if sampler else None
-    launches = eng.launch_count - launches0
-    ksum, kt_list = kernel_times()
+    launches, ksum, kt_list = per_step[-1]
     eng.enable_timing(False)
 
     lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
