@@ -32,6 +32,7 @@ SIGNATURES = {
     "cglb_kmv_sym_f32": (c_int, [C.c_void_p, c_int, c_dp, c_long, c_int, c_dp, c_dp, c_dbl, c_dbl, c_int, c_int, C.c_void_p]),
     "cglb_kmv_bwd_sym_f32": (c_int, [C.c_void_p, c_int, c_dp, c_dp, c_long, c_int, c_dp, c_dp, c_dbl, c_dp, c_dp, c_int, c_int, C.c_void_p]),
     "cglb_kmv_sym": (c_int, [C.c_void_p, c_int, c_dp, c_long, c_int, c_dp, c_dp, c_dbl, c_dbl, c_int, c_int, C.c_void_p]),
+    "cglb_kmv_sym_multi": (c_int, [C.c_void_p, c_int, c_dp, c_long, c_int, c_dp, c_int, c_dp, c_dbl, c_dbl, c_int, c_int, C.c_void_p]),
     "cglb_kmv_rect": (c_int, [C.c_void_p, c_int, c_dp, c_long, c_dp, c_long, c_int, c_dp, c_dp, c_dbl, C.c_void_p]),
     "cglb_kmv_bwd_sym": (c_int, [C.c_void_p, c_int, c_dp, c_long, c_int, c_dp, c_dp, c_dbl, c_dp, c_dp, c_int, c_int, C.c_void_p]),
     "cglb_knm_build": (c_int, [C.c_void_p, c_int, c_dp, c_long, c_dp, c_long, c_int, c_dbl, c_dp, c_long, C.c_void_p]),

@@ -41,8 +41,19 @@ class ShardedKernelMatvec:
         return self
 
     def __matmul__(self, v: Tensor) -> Tensor:
+        """`A @ x` for x of shape [n] / [n, 1] (one sweep) or [n, t] (conjugate_gradient.py:57,66,72: "[N, t]"): the block
+        goes through the multi-RHS sweep, which evaluates every kernel pair once for all t columns."""
+        vd = v.detach()
+        if vd.dim() == 2 and vd.shape[1] > 1:
+            if self.xpf is None and self.d <= 32:
+                y = self.eng.kmv_sym_multi(self.kind, self.xp, self.n, self.d, vd.contiguous(), self.variance, self.diag,
+                                           part=self.shard.rank, nparts=self.shard.world)
+                self.shard.all_reduce(y)
+                self.count += 1
+                return y
+            return torch.stack([(self @ vd[:, j]).reshape(-1) for j in range(vd.shape[1])], dim=1)      # wide / fp32-pair inputs
         sweep = self.eng.kmv_sym if self.xpf is None else self.eng.kmv_sym_f32
-        y = sweep(self.kind, self.xp if self.xpf is None else self.xpf, self.n, self.d, v.detach().reshape(-1).contiguous(),
+        y = sweep(self.kind, self.xp if self.xpf is None else self.xpf, self.n, self.d, vd.reshape(-1).contiguous(),
                   self.variance, self.diag, part=self.shard.rank, nparts=self.shard.world)
         self.shard.all_reduce(y)
         self.count += 1
@@ -101,7 +112,10 @@ class BoundEvaluator:
         self._T = None
         self.terms: Optional[CommonTermsDev] = None
         self._packed_key = None
-        # False: recompute K v, r and P r after the CG solve as models.py:280-282 does (one more n^2 sweep)
+        # True (default): K v, r and P r after the CG solve come from the final CG state (k + 1 + floor(k/restart) sweeps per
+        # evaluation).  False (CGLB_RECOMPUTE_RESIDUAL=1): recompute them as models.py:280-282 does (one more n^2 sweep).
+        # Both routes are compared with the reference's golden vectors at the north_star tolerance (1e-7); with the
+        # fixed-order reductions they return the same v, and their gradients differ by ~1e-14 (profiles/grad_spread_r02.md).
         self.reuse_cg_state = os.environ.get("CGLB_RECOMPUTE_RESIDUAL", "0") in ("", "0")
 
     def refresh_data(self, x: Tensor, y: Tensor):

@@ -54,6 +54,10 @@ struct Context {
     long vpad_cap;
     double* scratch;      // generic scratch (partials of reductions)
     long scratch_cap;
+    // deterministic accumulation (DESIGN.md "fixed-order reductions"): every CTA of a sweep adds into its OWN copy of the
+    // output vector (ypart + blockIdx.x * stride), a second kernel sums the copies in CTA order
+    double* ypart;        // [ypart_cap]
+    long ypart_cap;
     double* exp_table;    // [64] 2^(j/64) followed by [1024] 2^(j/1024); staged into shared memory by the kernels
     unsigned long long launches;   // number of kernels this context launched (bench.py gpu_launches)
 };
@@ -63,6 +67,7 @@ struct Context {
 constexpr int kScratchScalars = 256;
 int ensure_vpad(Context* ctx, long n_pad);
 int ensure_scratch(Context* ctx, long n_doubles);
+int ensure_ypart(Context* ctx, long n_doubles);
 
 // ---------------------------------------------------------------------------------------------
 // packed input layout (see DESIGN.md "data layout")

@@ -45,6 +45,18 @@ int ensure_scratch(Context* ctx, long n_doubles) {
     return CGLB_OK;
 }
 
+int ensure_ypart(Context* ctx, long n_doubles) {
+    if (n_doubles <= ctx->ypart_cap) return CGLB_OK;
+    CGLB_CUDA_OK(cudaDeviceSynchronize());
+    if (ctx->ypart) cudaFree(ctx->ypart);
+    ctx->ypart = nullptr;
+    ctx->ypart_cap = 0;
+    long cap = n_doubles + n_doubles / 16 + 1024;
+    CGLB_CUDA_OK(cudaMalloc(&ctx->ypart, sizeof(double) * cap));
+    ctx->ypart_cap = cap;
+    return CGLB_OK;
+}
+
 }  // namespace cglb
 
 using namespace cglb;
@@ -99,6 +111,7 @@ extern "C" int cglb_destroy(cglb_context* c) {
     if (ctx->upad) cudaFree(ctx->upad);
     if (ctx->rsum) cudaFree(ctx->rsum);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->ypart) cudaFree(ctx->ypart);
     if (ctx->exp_table) cudaFree(ctx->exp_table);
     delete ctx;
     return CGLB_OK;

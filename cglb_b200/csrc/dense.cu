@@ -1,7 +1,7 @@
 // K5 / K6: dense FP64 linear algebra for the Nystrom preconditioner and log-det terms, sm_100a.
 //
 //   cglb_gemm             C = alpha A op(B) + beta C           DMMA.8x8x4 tiles, cp.async 3-stage ring
-//   cglb_syrk             C = A A^T (split-K, lower tiles + mirror, RED.ADD.F64)
+//   cglb_syrk             C = A A^T (split-K, lower tiles + mirror; the K slices are summed in slice order)
 //   cglb_potrf            blocked right-looking Cholesky (128-wide panels)
 //   cglb_tri_inverse      L^-1 through inverted diagonal blocks + GEMMs
 //   cglb_trsm_left_lower  B <- alpha L^-1 B, one GEMM per 128-row block against [ -D^-1 L | alpha D^-1 ]
@@ -45,6 +45,9 @@ struct GemmArgs {
     double alpha, beta;
     int lower_only;       // skip tiles strictly above the block diagonal
     KEpiArgs ke;
+    // split-K (EPI_ATOMIC / EPI_SYRK): slice z stores alpha * (its partial product) at part + z * part_stride, row pitch n;
+    // splitk_reduce_kernel sums the slices in slice order (fixed summation order, no atomics)
+    double* part; long part_stride;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
@@ -284,13 +287,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
             for (int e = 0; e < 2; ++e) {
                 const long cc = col + e;
                 if (cc >= p.n) continue;
-                const double val = p.alpha * acc[i][j][e];
-                if (EPI == EPI_ATOMIC) {
-                    atomicAdd(p.C + row * p.ldc + cc, val);
-                } else {
-                    atomicAdd(p.C + row * p.ldc + cc, val);
-                    if (bm != bn) atomicAdd(p.C + cc * p.ldc + row, val);
-                }
+                p.part[(long)blockIdx.z * p.part_stride + row * p.n + cc] = p.alpha * acc[i][j][e];
             }
         }
     }
@@ -313,15 +310,35 @@ static int launch_gemm(Context* ctx, const GemmArgs& p, int ksplit, cudaStream_t
     return CGLB_OK;
 }
 
-__global__ void scale_matrix_kernel(double* c, long m, long n, long ldc, double beta) {
-    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+// C = beta C + sum_z part[z]  (slices in order);  sym: only col <= row is computed (lower tiles) and mirrored
+__global__ void splitk_reduce_kernel(const double* __restrict__ part, long part_stride, int ksplit, long m, long n,
+                                     double* __restrict__ c, long ldc, double beta, int sym) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= m * n) return;
-    double* p = c + (idx / n) * ldc + idx % n;
-    *p = (beta == 0.0) ? 0.0 : beta * *p;
+    const long row = idx / n, col = idx % n;
+    if (sym && col > row) return;
+    double s = (beta == 0.0) ? 0.0 : beta * c[row * ldc + col];
+    for (int z = 0; z < ksplit; ++z) s += part[(long)z * part_stride + idx];
+    c[row * ldc + col] = s;
+    if (sym && col != row) c[col * ldc + row] = s;
+}
+
+template <bool TRANSB, int EPI>
+static int launch_gemm_splitk(Context* ctx, GemmArgs p, int ksplit, int sym, cudaStream_t st) {
+    p.part_stride = p.m * p.n;
+    int rc = ensure_ypart(ctx, (long)ksplit * p.part_stride);
+    if (rc) return rc;
+    p.part = ctx->ypart;
+    rc = launch_gemm<TRANSB, EPI>(ctx, p, ksplit, st);
+    if (rc) return rc;
+    splitk_reduce_kernel<<<(unsigned)((p.m * p.n + 255) / 256), 256, 0, st>>>(p.part, p.part_stride, ksplit, p.m, p.n, p.C, p.ldc, p.beta, sym);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
 }
 
 // C = alpha A op(B) + beta C where C does not alias A or B: few output tiles and a long K are split over
-// blockIdx.z (C pre-scaled by beta, partial products accumulated with RED.ADD.F64) so that all SMs work.
+// blockIdx.z (every slice stores its partial product, summed in slice order afterwards) so that all SMs work.
 template <bool TRANSB>
 static int launch_gemm_auto(Context* ctx, GemmArgs p, cudaStream_t st) {
     const long tiles = ((p.m + GM - 1) / GM) * ((p.n + GN - 1) / GN);
@@ -332,12 +349,9 @@ static int launch_gemm_auto(Context* ctx, GemmArgs p, cudaStream_t st) {
         if (ksplit > max_split) ksplit = max_split;
     }
     if (ksplit <= 1) return launch_gemm<TRANSB, EPI_STORE>(ctx, p, 1, st);
-    scale_matrix_kernel<<<(unsigned)((p.m * p.n + 255) / 256), 256, 0, st>>>(p.C, p.m, p.n, p.ldc, p.beta);
-    ctx->launches++;
-    CGLB_LAUNCH_OK();
     p.k_chunk = ((p.k + ksplit - 1) / ksplit + GK - 1) / GK * GK;
     ksplit = (p.k + p.k_chunk - 1) / p.k_chunk;
-    return launch_gemm<TRANSB, EPI_ATOMIC>(ctx, p, (int)ksplit, st);
+    return launch_gemm_splitk<TRANSB, EPI_ATOMIC>(ctx, p, (int)ksplit, 0, st);
 }
 
 static int gemm_checked(Context* ctx, int transb, long m, long n, long k, double alpha, const double* a, long lda,
@@ -687,7 +701,7 @@ int knm_backward_wide(Context* ctx, int kind, const double* zp, long m, const do
     long chunk = ((ncols + ksplit - 1) / ksplit + GK - 1) / GK * GK;
     ksplit = (ncols + chunk - 1) / chunk;
     GemmArgs pg{t, ldt, xp, w, gx, kp, m, kp, ncols, chunk, 1.0, 0.0, 0, {}};
-    rc = launch_gemm<false, EPI_ATOMIC>(ctx, pg, (int)ksplit, st);
+    rc = launch_gemm_splitk<false, EPI_ATOMIC>(ctx, pg, (int)ksplit, 0, st);
     if (rc) return rc;
     const double cscale = (kind == CGLB_MATERN32) ? 1.7320508075688772935 : 0.70710678118654752440;
     knm_wide_assemble_kernel<<<d, 256, 0, st>>>(zp, m, xp, ncols, d, w, kp, rsum, csum, gx, gk, lengthscale, cscale, out_ls, out_var, out_z);
@@ -714,12 +728,14 @@ extern "C" int cglb_syrk(cglb_context* c, const double* a, long m, long n, long 
     CGLB_CHECK_ARG(ctx && a && cm, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (m == 0) return CGLB_OK;
-    if (!accumulate) {
-        set_zero_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, st>>>(cm, m, m, ldc);
-        ctx->launches++;
-        CGLB_LAUNCH_OK();
+    if (n == 0) {
+        if (!accumulate) {
+            set_zero_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, st>>>(cm, m, m, ldc);
+            ctx->launches++;
+            CGLB_LAUNCH_OK();
+        }
+        return CGLB_OK;
     }
-    if (n == 0) return CGLB_OK;
     long tiles_m = (m + GM - 1) / GM;
     long lower_tiles = tiles_m * (tiles_m + 1) / 2;
     // enough CTAs for ~4 waves, but at least 512 columns of K per chunk
@@ -730,8 +746,8 @@ extern "C" int cglb_syrk(cglb_context* c, const double* a, long m, long n, long 
     if (ksplit > 65535) ksplit = 65535;
     long chunk = ((n + ksplit - 1) / ksplit + GK - 1) / GK * GK;
     ksplit = (n + chunk - 1) / chunk;
-    GemmArgs p{a, lda, a, lda, cm, ldc, m, m, n, chunk, 1.0, 0.0, 1, {}};
-    return launch_gemm<true, EPI_SYRK>(ctx, p, (int)ksplit, st);
+    GemmArgs p{a, lda, a, lda, cm, ldc, m, m, n, chunk, 1.0, accumulate ? 1.0 : 0.0, 1, {}};
+    return launch_gemm_splitk<true, EPI_SYRK>(ctx, p, (int)ksplit, 1, st);
 }
 
 extern "C" int cglb_potrf(cglb_context* c, double* a, long m, long lda, int* info_dev, void* stream) {

@@ -90,8 +90,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepAr
     __shared__ double s_tab[kExpTabBig];                                  // static: LDS with an immediate base
     double* s_x = reinterpret_cast<double*>(smem_raw);                    // [DS_STAGES][kBJ*DP]
     double* s_v = s_x + DS_STAGES * kBJ * DP;                               // [DS_STAGES][kBJ]
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_v + DS_STAGES * kBJ);
+    double* s_slab = s_v + DS_STAGES * kBJ;                                 // [WARPS][chunk]: per-warp column sums of one item
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_slab + WARPS * Cur::DS_CHUNK);
     uint64_t* s_empty = s_full + DS_STAGES;
+    // Fixed summation order (no run-to-run differences): inside an item every warp parks its column sums in its own
+    // slab row; at the end of the item they are summed over the warps in warp order and added to THIS CTA's copy of y
+    // (args.y + blockIdx.x * ystride).  Two adds to one address come from the same thread (column j -> thread j % 256,
+    // row i -> its owner lane) or are separated by the CTA barriers at the end of an item; the copies are summed in CTA
+    // order by a second kernel.
+    double* const yb = args.y + (long)blockIdx.x * args.ystride;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
@@ -224,10 +231,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepAr
                         }
                     }
                     const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // = 2 j + e
-                    // every lane now holds one of the 32 column sums of this half tile (over the warp's rows):
-                    // one coalesced 256-byte RED per warp, no cross-warp reduction and no CTA barrier
-                    const long jc = j0 + half * 32 + (idx >> 1) * 8 + 2 * t4 + (idx & 1);
-                    if (jc < args.ncols) atomicAdd(args.y + jc, var * c8[0]);
+                    // every lane now holds one of the 32 column sums of this half tile (over the warp's rows): one
+                    // conflict-free 256-byte store into the warp's slab row, no CTA barrier inside the item
+                    s_slab[warp * Cur::DS_CHUNK + tile * kBJ + half * 32 + (idx >> 1) * 8 + 2 * t4 + (idx & 1)] = c8[0];
                 }
             }
             // this warp is done with the stage (the first n-tile of the next stage has been read already)
@@ -236,21 +242,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepAr
             stage = nstage;
             phase = nphase;
         }
+        // item end: column sums of the tiles beyond the row block, summed over the warps in warp order
+        __syncthreads();
+        for (int col = tid; col < ntiles * kBJ; col += DS_THREADS) {
+            const long jc = c0 + col;
+            if (c0 + (col & ~(kBJ - 1)) >= r0 + DS_ROWS && jc < args.ncols) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) s += s_slab[w * Cur::DS_CHUNK + col];
+                atomicAdd(yb + jc, var * s);
+            }
+        }
         // row sums: reduce over the 4 lanes sharing g; every warp owns its 32 rows
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
             double s = racc[i];
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (t4 == 0 && live[i]) atomicAdd(args.y + r0 + warp * WROWS + i * 8 + g, var * s);
+            if (t4 == 0 && live[i]) atomicAdd(yb + r0 + warp * WROWS + i * 8 + g, var * s);
         }
+        __syncthreads();      // the slab is free again; this item's adds precede the next item's
         cc.tau += gridDim.x;
         cc.load_item(args, n_chunks);
     }
 }
 
-static inline size_t dsweep_smem_bytes(int dp) {
-    return (size_t)(DS_STAGES * kBJ * dp + DS_STAGES * kBJ) * sizeof(double) + 2 * DS_STAGES * sizeof(uint64_t);
+static inline size_t dsweep_smem_bytes(int dp, int warps, int chunk) {
+    return (size_t)(DS_STAGES * kBJ * dp + DS_STAGES * kBJ + warps * chunk) * sizeof(double) + 2 * DS_STAGES * sizeof(uint64_t);
 }
 
 template <int KIND, int DP, int WARPS = 8, int MT = 4>
@@ -261,7 +279,7 @@ static int run_dsweep(Context* ctx, SweepArgs a, cudaStream_t st) {
     a.nb_cols = n_chunks;
     a.nitems = DS_RPC * n_chunks * (n_chunks + 1) / 2;
     auto kern = dmma_sweep_kernel<KIND, DP, WARPS, MT>;
-    const size_t smem = dsweep_smem_bytes(DP);
+    const size_t smem = dsweep_smem_bytes(DP, WARPS, CHUNK);
     CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
     if (my_items <= 0) return CGLB_OK;
@@ -298,7 +316,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_bwd_kernel(const SweepArgs
     __shared__ double s_red[WARPS][4 * NQ + 1];
     double* s_x = reinterpret_cast<double*>(smem_raw);                    // [DS_STAGES][kBJ*DP]
     double* s_wu = s_x + DS_STAGES * kBJ * DP;                            // [DS_STAGES][2][kBJ]  (w, u)
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_wu + DS_STAGES * 2 * kBJ);
+    double* s_slab = s_wu + DS_STAGES * 2 * kBJ;                          // [WARPS][chunk] per-warp column sums of one item
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_slab + WARPS * Cur::DS_CHUNK);
     uint64_t* s_empty = s_full + DS_STAGES;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -435,22 +454,34 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_bwd_kernel(const SweepArgs
                         }
                     }
                     const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                    const long jc = j0 + hh * 32 + (idx >> 1) * 8 + 2 * t4 + (idx & 1);
-                    if (jc < args.ncols) atomicAdd(args.y + jc, c8[0]);
+                    s_slab[warp * Cur::DS_CHUNK + tile * kBJ + hh * 32 + (idx >> 1) * 8 + 2 * t4 + (idx & 1)] = c8[0];
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[stage]);
             if (++stage == DS_STAGES) { stage = 0; phase ^= 1; }
         }
-        // item end: row sums (over the 4 lanes sharing g) and the cross term X_q = sum_i a_iq Y_iq
+        // item end: column sums of the tiles beyond the row block, summed over the warps in warp order and added to this
+        // CTA's copy of R (fixed order, see dmma_sweep_kernel; the pointer is formed here: no register is left in the loop)
+        __syncthreads();
+        double* const yb = args.y + (long)blockIdx.x * args.ystride;
+        for (int col = tid; col < ntiles * kBJ; col += DS_THREADS) {
+            const long jc = c0 + col;
+            if (c0 + (col & ~(kBJ - 1)) >= r0 + DS_ROWS && jc < args.ncols) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) s += s_slab[w * Cur::DS_CHUNK + col];
+                atomicAdd(yb + jc, s);
+            }
+        }
+        // row sums (over the 4 lanes sharing g) and the cross term X_q = sum_i a_iq Y_iq
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
             double s = racc[i];
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             const long row = r0 + warp * WROWS + i * 8 + g;
-            if (t4 == 0 && live[i]) atomicAdd(args.y + row, s);
+            if (t4 == 0 && live[i]) atomicAdd(yb + row, s);
             if (live[i]) {
                 const double* src = args.xp_rows + row * DP;
 #pragma unroll
@@ -462,6 +493,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_bwd_kernel(const SweepArgs
                     }
             }
         }
+        __syncthreads();
         cc.tau += gridDim.x;
         cc.load_item(args, n_chunks);
     }
@@ -491,14 +523,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_bwd_kernel(const SweepArgs
         }
     }
     __syncthreads();
+    double* const gb = args.gout + (long)blockIdx.x * args.gstride;       // this CTA's slot (summed in CTA order afterwards)
     if (tid < D) {
         double s = 0.0;
         for (int w = 0; w < WARPS; ++w) s += s_q[w][tid];
-        atomicAdd(args.gout + tid, s);
+        gb[tid] = s;
     } else if (tid == D) {
         double s = 0.0;
         for (int w = 0; w < WARPS; ++w) s += s_red[w][4 * NQ];
-        atomicAdd(args.gout + D, s);
+        gb[D] = s;
     }
 }
 
@@ -511,7 +544,7 @@ static int run_dbwd(Context* ctx, SweepArgs a, cudaStream_t st) {
     a.nb_cols = n_chunks;
     a.nitems = DS_RPC * n_chunks * (n_chunks + 1) / 2;
     auto kern = dmma_bwd_kernel<KIND, D, WARPS, MT>;
-    const size_t smem = (size_t)(DS_STAGES * kBJ * DP + DS_STAGES * 2 * kBJ) * sizeof(double) + 2 * DS_STAGES * sizeof(uint64_t);
+    const size_t smem = (size_t)(DS_STAGES * kBJ * DP + DS_STAGES * 2 * kBJ + WARPS * CHUNK) * sizeof(double) + 2 * DS_STAGES * sizeof(uint64_t);
     CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
     if (my_items <= 0) return CGLB_OK;

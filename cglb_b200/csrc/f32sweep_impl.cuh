@@ -26,7 +26,8 @@ __host__ __device__ inline int packed_width_f32(int d) { return (d + 4) & ~3; }
 struct SweepArgsF32 {
     const float* xp;         // packed fp32 rows/cols [n_pad][DPF]
     const float* vcol;       // v rounded to float, padded
-    double* y;               // output (atomically accumulated)
+    double* y;               // output: CTA b accumulates into y + b * ystride (fixed order, see kmv_impl.cuh)
+    long ystride;
     long n;
     long nb;                 // number of BI blocks
     long nitems;
@@ -210,14 +211,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) f32_sweep_kernel(const SweepArg
                     double s = 0.0;
 #pragma unroll
                     for (int w = 0; w < WARPS; ++w) s += (double)s_col[(colbuf * WARPS + w) * kBJ + tid];
-                    if (j < args.n) atomicAdd(args.y + j, var * s);
+                    if (j < args.n) atomicAdd(args.y + (long)blockIdx.x * args.ystride + j, var * s);
                 }
                 colbuf ^= 1;
             }
         }
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti)
-            if (live[ti]) atomicAdd(args.y + r0 + ti * kThreads + tid, var * racc[ti]);
+            if (live[ti]) atomicAdd(args.y + (long)blockIdx.x * args.ystride + r0 + ti * kThreads + tid, var * racc[ti]);
+        __syncthreads();
         cc.tau += gridDim.x;
         load_item(cc);
     }
@@ -231,8 +233,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) f32_sweep_kernel(const SweepArg
 struct BwdArgsF32 {
     const float* xp;                       // packed fp32 [n_pad][DPF]
     const float* wcol; const float* ucol;  // padded float copies of w and u
-    double* rsum;                          // R (atomics)
-    double* gout;                          // [D+1]: -2 X_q ..., variance sum
+    double* rsum;                          // R: CTA b accumulates into rsum + b * ystride
+    double* gout;                          // [D+1]: -2 X_q ..., variance sum of CTA b at gout + b * gstride
+    long ystride, gstride;
     long n, nb, nitems;
     int part, nparts;
 };
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) f32_bwd_kernel(const BwdArgsF32
                     double s = 0.0;
 #pragma unroll
                     for (int w = 0; w < WARPS; ++w) s += (double)s_col[(colbuf * WARPS + w) * kBJ + tid];
-                    if (j < args.n) atomicAdd(args.rsum + j, s);
+                    if (j < args.n) atomicAdd(args.rsum + (long)blockIdx.x * args.ystride + j, s);
                 }
                 colbuf ^= 1;
             }
@@ -419,7 +422,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) f32_bwd_kernel(const BwdArgsF32
         const double rscale = offdiag ? 1.0 : 2.0;
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti)
-            if (live[ti]) atomicAdd(args.rsum + r0 + ti * kThreads + tid, rscale * racc[ti]);
+            if (live[ti]) atomicAdd(args.rsum + (long)blockIdx.x * args.ystride + r0 + ti * kThreads + tid, rscale * racc[ti]);
+        __syncthreads();
         cc.tau += gridDim.x;
         load_item(cc);
     }
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) f32_bwd_kernel(const BwdArgsF32
     if (tid <= D) {
         double s = 0.0;
         for (int w = 0; w < WARPS; ++w) s += s_red[w * (D + 2) + tid];
-        atomicAdd(args.gout + tid, s);
+        args.gout[(long)blockIdx.x * args.gstride + tid] = s;
     }
 }
 

@@ -86,6 +86,58 @@ __global__ void bwd_prologue_kernel(const double* __restrict__ u, const double* 
     }
 }
 
+// Vpad[i][r] = V[i][r] for r < t, 0 for t <= r < T and for padded rows (multi-RHS sweep: T = 2 or 4 columns per group)
+__global__ void multi_prologue_kernel(const double* __restrict__ v, long n, long n_pad, int t, int t0, int T, double* __restrict__ vpad) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_pad * T) return;
+    const long i = idx / T;
+    const int r = (int)(idx % T);
+    vpad[idx] = (i < n && t0 + r < t) ? v[i * t + t0 + r] : 0.0;
+}
+
+// Y[i][t0 + r] = diag * V[i][t0 + r] + sum_c part[c][i][r]   (fixed CTA order)
+__global__ void multi_reduce_kernel(const double* __restrict__ part, long stride, int nslots, const double* __restrict__ v, double diag,
+                                    double* __restrict__ y, long n, int t, int t0, int T) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * T) return;
+    const long i = idx / T;
+    const int r = (int)(idx % T);
+    if (t0 + r >= t) return;
+    double s = diag * v[i * t + t0 + r];
+#pragma unroll 8
+    for (int c = 0; c < nslots; ++c) s += part[(long)c * stride + idx];
+    y[i * t + t0 + r] = s;
+}
+
+// Second stage of the fixed-order reductions: the sweeps' CTAs accumulate into their own copies of the output vector
+// (part + c * stride); here the copies are summed in CTA order.  y[i] = diag * v[i] + sum_c part[c][i].
+__global__ void reduce_parts_kernel(const double* __restrict__ part, long stride, int nslots, const double* __restrict__ v,
+                                    double diag, double* __restrict__ y, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = (v != nullptr) ? diag * v[i] : 0.0;
+#pragma unroll 8
+    for (int c = 0; c < nslots; ++c) s += part[(long)c * stride + i];
+    y[i] = s;
+}
+
+// backward sweep: R[i] = sum_c part[c][i]; the last block also sums the per-CTA gradient slots into gtmp[0 .. d]
+__global__ void reduce_bwd_parts_kernel(const double* __restrict__ part, long stride, int nslots, double* __restrict__ rsum, long n,
+                                        const double* __restrict__ gpart, long gstride, int d, double* __restrict__ gtmp) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < nslots; ++c) s += part[(long)c * stride + i];
+        rsum[i] = s;
+    }
+    if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x <= d) {
+        double s = 0.0;
+        for (int c = 0; c < nslots; ++c) s += gpart[(long)c * gstride + threadIdx.x];
+        gtmp[threadIdx.x] = s;
+    }
+}
+
 // out[q] += (variance*cfac/ls_q) * ( sum_i a_iq^2 R_i + gq[q] ) ; out[d] += gvar      (single CTA per q chunk)
 __global__ void bwd_epilogue_kernel(const double* __restrict__ xp, long n, int d, int dp, const double* __restrict__ rsum,
                                     const double* __restrict__ gtmp, const double* __restrict__ ls, double variance,
@@ -180,10 +232,10 @@ int knm_backward_wide(Context* ctx, int kind, const double* zp, long m, const do
                       const double* lengthscale, double* t, long ldt, const double* wt, const double* zvec, double* out_ls,
                       double* out_var, double* out_z, cudaStream_t st);
 int wide_sweep(Context* ctx, int kind, bool sym, const double* xp_rows, long nrows, const double* xp_cols, long ncols, int d,
-               const double* vcol, double* y, double variance, int part, int nparts, cudaStream_t st);
+               const double* vcol, double* y, long ystride, double variance, int part, int nparts, cudaStream_t st);
 
 int wide_bwd_sweep(Context* ctx, int kind, const double* xp, long n, int d, const double* wcol, const double* ucol, double* rsum,
-                   double* gout, int part, int nparts, cudaStream_t st);
+                   long ystride, double* gout, long gstride, int part, int nparts, cudaStream_t st);
 
 bool dsweep_supported(const Context* ctx, int d, long n, int nparts);
 bool dbwd_supported(const Context* ctx, int d, long n, int nparts);
@@ -205,9 +257,10 @@ static int dispatch(Context* ctx, int kind, int d, int mode, const SweepArgs& a,
         if (dm != 0 && dbwd_supported(ctx, d, a.nrows, dm == 2 ? 0 : a.nparts)) mode = 4;
     }
     if (d > CGLB_MAX_REGISTER_D && mode == 2)
-        return wide_bwd_sweep(ctx, kind, a.xp_rows, a.nrows, d, a.vcol, a.ucol, a.y, a.gout, a.part, a.nparts, st);
+        return wide_bwd_sweep(ctx, kind, a.xp_rows, a.nrows, d, a.vcol, a.ucol, a.y, a.ystride, a.gout, a.gstride, a.part, a.nparts, st);
     if (d > CGLB_MAX_REGISTER_D)
-        return wide_sweep(ctx, kind, mode == 0, a.xp_rows, a.nrows, a.xp_cols, a.ncols, d, a.vcol, a.y, a.variance, a.part, a.nparts, st);
+        return wide_sweep(ctx, kind, mode == 0, a.xp_rows, a.nrows, a.xp_cols, a.ncols, d, a.vcol, a.y, a.ystride, a.variance, a.part,
+                          a.nparts, st);
     sweep_fn f = get_sweep_fn(d);
     if (!f) {
         set_error("kernel sweep: d=%d has no register-resident instantiation in this build", d);
@@ -273,12 +326,21 @@ extern "C" int cglb_kmv_sym_f32(cglb_context* c, int kind, const float* xpf, lon
     int rc = ensure_vpad(ctx, v_pad);                     // the float copy of v lives in the (double) u workspace
     if (rc) return rc;
     float* vpad32 = reinterpret_cast<float*>(ctx->upad);
+    const int nslots = ctx->num_sms;
+    rc = ensure_ypart(ctx, (long)nslots * v_pad);
+    if (rc) return rc;
+    CGLB_CUDA_OK(cudaMemsetAsync(ctx->ypart, 0, sizeof(double) * nslots * v_pad, st));
     kmv_prologue_f32_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(v, n, v_pad, vpad32, y, part == 0 ? diag : 0.0);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     SweepArgsF32 a{};
-    a.xp = xpf; a.vcol = vpad32; a.y = y; a.n = n; a.variance = variance; a.part = part; a.nparts = nparts;
-    return f(ctx, kind, a, st);
+    a.xp = xpf; a.vcol = vpad32; a.y = ctx->ypart; a.ystride = v_pad; a.n = n; a.variance = variance; a.part = part; a.nparts = nparts;
+    rc = f(ctx, kind, a, st);
+    if (rc) return rc;
+    reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->ypart, v_pad, nslots, v, part == 0 ? diag : 0.0, y, n);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
 }
 
 extern "C" int cglb_kmv_bwd_sym_f32(cglb_context* c, int kind, const float* xpf, const double* xp, long n, int d, const double* u,
@@ -307,11 +369,20 @@ extern "C" int cglb_kmv_bwd_sym_f32(cglb_context* c, int kind, const float* xpf,
     bwd_prologue_f32_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(u, w, n, v_pad, upad32, wpad32, ctx->rsum);
     ctx->launches++;
     CGLB_LAUNCH_OK();
-    CGLB_CUDA_OK(cudaMemsetAsync(ctx->scratch, 0, sizeof(double) * kScratchScalars, st));
+    const int nslots = ctx->num_sms;
+    rc = ensure_ypart(ctx, (long)nslots * (v_pad + kScratchScalars));
+    if (rc) return rc;
+    CGLB_CUDA_OK(cudaMemsetAsync(ctx->ypart, 0, sizeof(double) * nslots * (v_pad + kScratchScalars), st));
+    double* gpart = ctx->ypart + (long)nslots * v_pad;
     BwdArgsF32 a{};
-    a.xp = xpf; a.wcol = wpad32; a.ucol = upad32; a.rsum = ctx->rsum; a.gout = ctx->scratch; a.n = n; a.part = part; a.nparts = nparts;
+    a.xp = xpf; a.wcol = wpad32; a.ucol = upad32; a.rsum = ctx->ypart; a.ystride = v_pad; a.gout = gpart; a.gstride = kScratchScalars;
+    a.n = n; a.part = part; a.nparts = nparts;
     rc = f(ctx, kind, a, st);
     if (rc) return rc;
+    reduce_bwd_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->ypart, v_pad, nslots, ctx->rsum, n, gpart, kScratchScalars, d,
+                                                                          ctx->scratch);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
     const double cfac = (kind == CGLB_MATERN32) ? 1.0 : 2.0;
     bwd_epilogue_kernel<<<d, 256, 0, st>>>(xp, n, d, packed_width(d), ctx->rsum, ctx->scratch, lengthscale, variance, cfac, out, 1);
     ctx->launches++;
@@ -342,13 +413,70 @@ extern "C" int cglb_kmv_sym(cglb_context* c, int kind, const double* xp, long n,
     int rc = ensure_vpad(ctx, v_pad);
     if (rc) return rc;
     (void)n_pad;
-    kmv_prologue_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(v, n, v_pad, ctx->vpad, y, n, part == 0 ? diag : 0.0);
+    // fixed summation order: one copy of y per CTA slot (zeroed here), summed in slot order after the sweep
+    const int nslots = ctx->num_sms;
+    rc = ensure_ypart(ctx, (long)nslots * v_pad);
+    if (rc) return rc;
+    CGLB_CUDA_OK(cudaMemsetAsync(ctx->ypart, 0, sizeof(double) * nslots * v_pad, st));
+    kmv_prologue_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(v, n, v_pad, ctx->vpad, nullptr, 0, 0.0);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     SweepArgs a{};
-    a.xp_rows = xp; a.xp_cols = xp; a.vcol = ctx->vpad; a.ucol = nullptr; a.y = y; a.gout = nullptr;
+    a.xp_rows = xp; a.xp_cols = xp; a.vcol = ctx->vpad; a.ucol = nullptr; a.y = ctx->ypart; a.ystride = v_pad; a.gout = nullptr;
     a.nrows = n; a.ncols = n; a.exp_tab = ctx->exp_table; a.variance = variance; a.part = part; a.nparts = nparts;
-    return dispatch(ctx, kind, d, 0, a, st);
+    rc = dispatch(ctx, kind, d, 0, a, st);
+    if (rc) return rc;
+    reduce_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->ypart, v_pad, nslots, v, part == 0 ? diag : 0.0, y, n);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
+}
+
+extern "C" int cglb_kmv_sym_multi(cglb_context* c, int kind, const double* xp, long n, int d, const double* v, int t, double* y,
+                                  double variance, double diag, int part, int nparts, void* stream) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx != nullptr, "null context");
+    CGLB_CHECK_ARG(nparts >= 1 && part >= 0 && part < nparts, "part/nparts");
+    CGLB_CHECK_ARG(kind == CGLB_MATERN32 || kind == CGLB_RBF, "kernel kind");
+    CGLB_CHECK_ARG(t >= 1, "t >= 1 right-hand sides");
+    if (n == 0) return CGLB_OK;
+    CGLB_CHECK_ARG(xp && v && y, "null pointer");
+    if (t == 1) return cglb_kmv_sym(c, kind, xp, n, d, v, y, variance, diag, part, nparts, stream);
+    if (d > CGLB_MAX_REGISTER_D) {
+        set_error("cglb_kmv_sym_multi: d=%d > %d (wide inputs): call cglb_kmv_sym once per right-hand side", d, CGLB_MAX_REGISTER_D);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    sweep_fn f = get_sweep_fn(d);
+    if (!f) {
+        set_error("kernel sweep: d=%d has no register-resident instantiation in this build", d);
+        return CGLB_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long v_pad = (n + 1023) / 1024 * 1024;
+    const int nslots = ctx->num_sms;
+    // columns in groups of 4 (or 2 for a last pair): one sweep per group, every kernel pair evaluated once per group
+    for (int t0 = 0; t0 < t;) {
+        const int T = (t - t0 > 2) ? 4 : 2;
+        int rc = ensure_vpad(ctx, v_pad * T);
+        if (rc) return rc;
+        rc = ensure_ypart(ctx, (long)nslots * v_pad * T);
+        if (rc) return rc;
+        CGLB_CUDA_OK(cudaMemsetAsync(ctx->ypart, 0, sizeof(double) * nslots * v_pad * T, st));
+        multi_prologue_kernel<<<(unsigned)((v_pad * T + 255) / 256), 256, 0, st>>>(v, n, v_pad, t, t0, T, ctx->vpad);
+        ctx->launches++;
+        CGLB_LAUNCH_OK();
+        SweepArgs a{};
+        a.xp_rows = xp; a.xp_cols = xp; a.vcol = ctx->vpad; a.y = ctx->ypart; a.ystride = v_pad * T;
+        a.nrows = n; a.ncols = n; a.exp_tab = ctx->exp_table; a.variance = variance; a.part = part; a.nparts = nparts;
+        rc = f(ctx, kind, T == 2 ? 5 : 6, a, st);
+        if (rc) return rc;
+        multi_reduce_kernel<<<(unsigned)((n * T + 255) / 256), 256, 0, st>>>(ctx->ypart, v_pad * T, nslots, v, part == 0 ? diag : 0.0, y, n, t,
+                                                                               t0, T);
+        ctx->launches++;
+        CGLB_LAUNCH_OK();
+        t0 += T;
+    }
+    return CGLB_OK;
 }
 
 extern "C" int cglb_kmv_rect(cglb_context* c, int kind, const double* xp_rows, long nrows, const double* xp_cols,
@@ -365,12 +493,24 @@ extern "C" int cglb_kmv_rect(cglb_context* c, int kind, const double* xp_rows, l
     kmv_prologue_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(v, ncols, v_pad, ctx->vpad, nullptr, 0, 0.0);
     ctx->launches++;
     CGLB_LAUNCH_OK();
-    CGLB_CUDA_OK(cudaMemsetAsync(y, 0, sizeof(double) * nrows, st));
-    if (ncols == 0) return CGLB_OK;
+    if (ncols == 0) {
+        CGLB_CUDA_OK(cudaMemsetAsync(y, 0, sizeof(double) * nrows, st));
+        return CGLB_OK;
+    }
+    const int nslots = ctx->num_sms;
+    const long r_pad = (nrows + 7) / 8 * 8;
+    rc = ensure_ypart(ctx, (long)nslots * r_pad);
+    if (rc) return rc;
+    CGLB_CUDA_OK(cudaMemsetAsync(ctx->ypart, 0, sizeof(double) * nslots * r_pad, st));
     SweepArgs a{};
-    a.xp_rows = xp_rows; a.xp_cols = xp_cols; a.vcol = ctx->vpad; a.y = y;
+    a.xp_rows = xp_rows; a.xp_cols = xp_cols; a.vcol = ctx->vpad; a.y = ctx->ypart; a.ystride = r_pad;
     a.nrows = nrows; a.ncols = ncols; a.exp_tab = ctx->exp_table; a.variance = variance; a.part = 0; a.nparts = 1;
-    return dispatch(ctx, kind, d, 1, a, st);
+    rc = dispatch(ctx, kind, d, 1, a, st);
+    if (rc) return rc;
+    reduce_parts_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(ctx->ypart, r_pad, nslots, nullptr, 0.0, y, nrows);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    return CGLB_OK;
 }
 
 extern "C" int cglb_kmv_bwd_sym(cglb_context* c, int kind, const double* xp, long n, int d, const double* u,
@@ -392,12 +532,21 @@ extern "C" int cglb_kmv_bwd_sym(cglb_context* c, int kind, const double* xp, lon
     bwd_prologue_kernel<<<(unsigned)((v_pad + 255) / 256), 256, 0, st>>>(u, w, n, v_pad, ctx->upad, ctx->vpad, ctx->rsum);
     ctx->launches++;
     CGLB_LAUNCH_OK();
-    CGLB_CUDA_OK(cudaMemsetAsync(ctx->scratch, 0, sizeof(double) * kScratchScalars, st));
+    const int nslots = ctx->num_sms;
+    rc = ensure_ypart(ctx, (long)nslots * (v_pad + kScratchScalars));
+    if (rc) return rc;
+    CGLB_CUDA_OK(cudaMemsetAsync(ctx->ypart, 0, sizeof(double) * nslots * (v_pad + kScratchScalars), st));
+    double* gpart = ctx->ypart + (long)nslots * v_pad;
     SweepArgs a{};
-    a.xp_rows = xp; a.xp_cols = xp; a.vcol = ctx->vpad; a.ucol = ctx->upad; a.y = ctx->rsum; a.gout = ctx->scratch;
+    a.xp_rows = xp; a.xp_cols = xp; a.vcol = ctx->vpad; a.ucol = ctx->upad; a.y = ctx->ypart; a.ystride = v_pad;
+    a.gout = gpart; a.gstride = kScratchScalars;
     a.nrows = n; a.ncols = n; a.exp_tab = ctx->exp_table; a.variance = variance; a.part = part; a.nparts = nparts;
     rc = dispatch(ctx, kind, d, 2, a, st);
     if (rc) return rc;
+    reduce_bwd_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->ypart, v_pad, nslots, ctx->rsum, n, gpart, kScratchScalars, d,
+                                                                          ctx->scratch);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
     // dk/dl_q = variance * e' * delta_q^2 / l_q with e' = e^-s (Matern32) or 2 e^-q (RBF)
     const double cfac = (kind == CGLB_MATERN32) ? 1.0 : 2.0;
     bwd_epilogue_kernel<<<d, 256, 0, st>>>(xp, n, d, packed_width(d), ctx->rsum, ctx->scratch, lengthscale, variance, cfac, out, 1);

@@ -35,8 +35,10 @@ struct SweepArgs {
     const double* xp_cols;   // packed cols   [cols_pad][DP]
     const double* vcol;      // padded column vector (v for fwd; w for bwd)   [cols_pad]
     const double* ucol;      // bwd only: u on the column side                [cols_pad]
-    double* y;               // fwd: output (atomically accumulated); bwd: R row sums
-    double* gout;            // bwd: [D+1] accumulators (-2 X_q ..., variance sum)
+    double* y;               // fwd: output; bwd: R row sums.  CTA b accumulates into y + b * ystride (its own copy when
+                             // ystride > 0: deterministic, summed in CTA order afterwards; ystride = 0: one shared vector)
+    double* gout;            // bwd: [D+1] sums (-2 X_q ..., variance sum) of CTA b at gout + b * gstride (plain stores)
+    long ystride, gstride;
     long nrows, ncols;       // valid counts
     long nb_rows, nb_cols;   // number of BI blocks
     long nitems;             // total work items (global, before the part split)
@@ -249,6 +251,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_sweep_kernel(const SweepArg
     }
     int colbuf = 0;
     const double var = args.variance;
+    // Fixed summation order: all adds of this CTA go to its own copy of y.  Two adds to the same address are either issued
+    // by the same thread (column j -> thread j % 64, row i -> thread i % kThreads) or separated by a CTA barrier (the
+    // per-tile barrier below, the barrier at the end of every item), and the items of a CTA are a static sequence.
+    double* const yb = args.y + (long)blockIdx.x * args.ystride;
 
     while (cc.valid) {
         const bool offdiag = SYM && (cc.I != cc.C);
@@ -333,14 +339,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_sweep_kernel(const SweepArg
                     double s = 0.0;
 #pragma unroll
                     for (int w = 0; w < kWarps; ++w) s += s_col[(colbuf * kWarps + w) * kBJ + tid];
-                    if (j < args.ncols) atomicAdd(args.y + j, var * s);
+                    if (j < args.ncols) atomicAdd(yb + j, var * s);
                 }
                 colbuf ^= 1;
             }
         }
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti)
-            if (live[ti]) atomicAdd(args.y + r0 + ti * kThreads + tid, var * racc[ti]);
+            if (live[ti]) atomicAdd(yb + r0 + ti * kThreads + tid, var * racc[ti]);
+        if (SYM) __syncthreads();       // row adds of this item before the column adds of the next (fixed order)
         cc.next_item(args);
     }
 }
@@ -387,6 +394,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_bwd_kernel(const SweepArgs 
     double gq[D], gvar = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) gq[k] = 0.0;
+    double* const yb = args.y + (long)blockIdx.x * args.ystride;      // this CTA's copy of R (fixed order, see the forward sweep)
 
     while (cc.valid) {
         const bool offdiag = (cc.I != cc.C);
@@ -465,7 +473,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_bwd_kernel(const SweepArgs 
                     double s = 0.0;
 #pragma unroll
                     for (int w = 0; w < kWarps; ++w) s += s_col[(colbuf * kWarps + w) * kBJ + tid];
-                    if (j < args.ncols) atomicAdd(args.y + j, s);
+                    if (j < args.ncols) atomicAdd(yb + j, s);
                 }
                 colbuf ^= 1;
             }
@@ -473,7 +481,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_bwd_kernel(const SweepArgs 
         const double rscale = offdiag ? 1.0 : 2.0;
 #pragma unroll
         for (int ti = 0; ti < TI; ++ti)
-            if (live[ti]) atomicAdd(args.y + r0 + ti * kThreads + tid, rscale * racc[ti]);
+            if (live[ti]) atomicAdd(yb + r0 + ti * kThreads + tid, rscale * racc[ti]);
+        __syncthreads();
         cc.next_item(args);
     }
 
@@ -491,7 +500,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kmv_bwd_kernel(const SweepArgs 
     if (tid <= D) {
         double s = 0.0;
         for (int w = 0; w < kWarps; ++w) s += s_red[w * (D + 2) + tid];
-        atomicAdd(args.gout + tid, s);
+        args.gout[(long)blockIdx.x * args.gstride + tid] = s;
     }
 }
 
@@ -774,7 +783,7 @@ static int run_bwd(Context* ctx, const SweepArgs& a, cudaStream_t st) {
 #endif
 
 // dispatch table filled by the per-D translation units
-typedef int (*sweep_fn)(Context*, int kind, int mode /*0 sym fwd, 1 rect fwd, 2 sym bwd, 3 sym fwd on DMMA*/, const SweepArgs&, cudaStream_t);
+typedef int (*sweep_fn)(Context*, int kind, int mode /*0 sym fwd, 1 rect fwd, 2 sym bwd, 3 sym fwd on DMMA, 4 sym bwd on DMMA, 5/6 sym fwd with 2/4 right-hand sides*/, const SweepArgs&, cudaStream_t);
 typedef int (*knm_fn)(Context*, int kind, int bwd, const KnmArgs&, cudaStream_t);
 knm_fn get_knm_fn(int d);
 constexpr int kMaxRegisterD = 32;

@@ -3,6 +3,7 @@
 #include "kmv_impl.cuh"
 #include "dsweep_impl.cuh"
 #include "f32sweep_impl.cuh"
+#include "kmv_multi_impl.cuh"
 
 #ifndef CGLB_KMV_D
 #error "compile with -DCGLB_KMV_D=<d>"
@@ -32,6 +33,8 @@ int CGLB_CAT(sweep_d, CGLB_KMV_D)(Context* ctx, int kind, int mode, const SweepA
             return CGLB_ERR_UNSUPPORTED;
         }
     }
+    if (mode == 5) return kind == CGLB_MATERN32 ? run_multi<CGLB_MATERN32, D, 2>(ctx, a, st) : run_multi<CGLB_RBF, D, 2>(ctx, a, st);
+    if (mode == 6) return kind == CGLB_MATERN32 ? run_multi<CGLB_MATERN32, D, 4>(ctx, a, st) : run_multi<CGLB_RBF, D, 4>(ctx, a, st);
     if (kind == CGLB_MATERN32) {
         if (mode == 0) return run_fwd<CGLB_MATERN32, D, true>(ctx, a, st);
         if (mode == 1) return run_fwd<CGLB_MATERN32, D, false>(ctx, a, st);

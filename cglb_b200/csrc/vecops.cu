@@ -142,8 +142,18 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const double* __restrict
             for (int j = lane; j < cn; j += 32) acc0 = fma(ap[j], s_r[j], acc0);
         }
         const double s = warp_sum(acc0 + acc1);
-        if (lane == 0) atomicAdd(q + row, s);
+        if (lane == 0) q[(long)blockIdx.x * m + row] = s;      // partial of this column chunk; summed in chunk order below
     }
+}
+
+// q[row] = sum over the column chunks, in chunk order (fixed summation order)
+__global__ void __launch_bounds__(256) gemv_rows_reduce_kernel(const double* __restrict__ qpart, long nchunks, long m, double* __restrict__ q) {
+    const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= m) return;
+    double s = 0.0;
+#pragma unroll 8
+    for (long c = 0; c < nchunks; ++c) s += qpart[c * m + row];
+    q[row] = s;
 }
 
 // t = Linv q  (Linv lower triangular, m x m): one warp per row
@@ -164,9 +174,10 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
     if (lane == 0) t[row] = acc;
 }
 
-// w[c] += sum_{r in block} Linv[r][c] t[r]   for r >= c      grid (col blocks of 128, row blocks of 128)
+// wpart[rb][c] = sum_{r in row block rb} Linv[r][c] t[r]   for r >= c      grid (col blocks of 128, row blocks of 128);
+// the row-block partials are summed in block order by the consumer (gemv_cols_finish_kernel)
 __global__ void __launch_bounds__(128) trmv_lower_t_kernel(const double* __restrict__ linv, long m, const double* __restrict__ t,
-                                                           double* __restrict__ w) {
+                                                           double* __restrict__ wpart) {
     const long c = (long)blockIdx.x * 128 + threadIdx.x;
     const long r0 = (long)blockIdx.y * 128;
     if (blockIdx.y < blockIdx.x) return;      // block strictly above the diagonal: all zeros
@@ -177,16 +188,24 @@ __global__ void __launch_bounds__(128) trmv_lower_t_kernel(const double* __restr
     const long rend = (r0 + 128 < m) ? r0 + 128 : m;
     double acc = 0.0;
     for (long r = r0; r < rend; ++r) acc = fma(linv[r * m + c], s_t[r - r0], acc);
-    atomicAdd(w + c, acc);
+    wpart[(long)blockIdx.y * m + c] = acc;
 }
 
 // z[i] = (r[i] - sum_m A[m][i] w[m]) / sigma_sq ; rz += sum z r        thread = 2 columns
 __global__ void __launch_bounds__(128) gemv_cols_finish_kernel(const double* __restrict__ a, long m, long ncols, long lda,
-                                                               const double* __restrict__ w, const double* __restrict__ r,
-                                                               double inv_sigma_sq, double* __restrict__ z, double* rz) {
+                                                               const double* __restrict__ wpart, double* __restrict__ w_out,
+                                                               const double* __restrict__ r, double inv_sigma_sq,
+                                                               double* __restrict__ z, double* rz, double* partials, int* counter) {
     extern __shared__ __align__(16) double s_w[];      // [m]
     __shared__ double sh[32];
-    for (long i = threadIdx.x; i < m; i += blockDim.x) s_w[i] = w[i];
+    // w = LBinv^T t: row-block partials of trmv_lower_t_kernel (blocks rb >= c / 128 exist), summed in block order
+    const long nrb = (m + 127) / 128;
+    for (long i = threadIdx.x; i < m; i += blockDim.x) {
+        double s = 0.0;
+        for (long rb = i / 128; rb < nrb; ++rb) s += wpart[rb * m + i];
+        s_w[i] = s;
+        if (blockIdx.x == 0) w_out[i] = s;
+    }
     __syncthreads();
     const long c = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     const bool vec_ok = ((lda & 1) == 0) && (((uintptr_t)a & 15) == 0);
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(128) gemv_cols_finish_kernel(const double* __r
         }
     }
     part = block_sum(part, sh);
-    if (threadIdx.x == 0) atomicAdd(rz, part);
+    finish_reduction(part, partials, counter, rz, 1.0, sh);      // block partials summed in block order by the last block
 }
 
 static inline int red_blocks(long n) {
@@ -304,10 +323,19 @@ extern "C" int cglb_precond_project(cglb_context* c, const double* a, long m, lo
     Context* ctx = reinterpret_cast<Context*>(c);
     CGLB_CHECK_ARG(ctx && a && r && q, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    CGLB_CUDA_OK(cudaMemsetAsync(q, 0, sizeof(double) * m, st));
-    if (m == 0 || ncols == 0) return CGLB_OK;
-    dim3 grid((unsigned)((ncols + kGvCols - 1) / kGvCols), (unsigned)((m + kGvRows - 1) / kGvRows));
-    gemv_rows_kernel<<<grid, 256, 0, st>>>(a, m, ncols, lda, r, q);
+    if (m == 0) return CGLB_OK;
+    if (ncols == 0) {
+        CGLB_CUDA_OK(cudaMemsetAsync(q, 0, sizeof(double) * m, st));
+        return CGLB_OK;
+    }
+    const long nchunks = (ncols + kGvCols - 1) / kGvCols;
+    int rc = ensure_ypart(ctx, nchunks * m);
+    if (rc) return rc;
+    dim3 grid((unsigned)nchunks, (unsigned)((m + kGvRows - 1) / kGvRows));
+    gemv_rows_kernel<<<grid, 256, 0, st>>>(a, m, ncols, lda, r, ctx->ypart);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    gemv_rows_reduce_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ctx->ypart, nchunks, m, q);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;
@@ -323,22 +351,27 @@ extern "C" int cglb_precond_finish(cglb_context* c, const double* a, long m, lon
     int rc = ensure_scratch(ctx, kScratchScalars + kRedBlocks + m);
     if (rc) return rc;
     double* t = ctx->scratch + kScratchScalars + kRedBlocks;
+    // fixed-order partials: [row blocks][m] of w = LBinv^T t, then one r^T z partial per CTA of the finish kernel
+    const long nrb = (m + 127) / 128;
+    const long nfin = ncols > 0 ? (ncols + 255) / 256 : 1;      // a rank without columns still needs w = B^-1 A r (and r^T z = 0)
+    rc = ensure_ypart(ctx, nrb * m + nfin + 8);
+    if (rc) return rc;
+    double* wpart = ctx->ypart;
+    double* rzpart = ctx->ypart + nrb * m;
     if (m > 0) {
-        // t = LBinv q ; also clears w_out and *rz_dev
-        trmv_lower_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(lbinv, m, q, t, w_out, m, rz_dev);
+        // t = LBinv q
+        trmv_lower_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(lbinv, m, q, t, nullptr, 0, nullptr);
         ctx->launches++;
         CGLB_LAUNCH_OK();
-        dim3 g2((unsigned)((m + 127) / 128), (unsigned)((m + 127) / 128));
-        trmv_lower_t_kernel<<<g2, 128, 0, st>>>(lbinv, m, t, w_out);
+        dim3 g2((unsigned)nrb, (unsigned)nrb);
+        trmv_lower_t_kernel<<<g2, 128, 0, st>>>(lbinv, m, t, wpart);
         ctx->launches++;
         CGLB_LAUNCH_OK();
-    } else {
-        CGLB_CUDA_OK(cudaMemsetAsync(rz_dev, 0, sizeof(double), st));
     }
-    if (ncols == 0) return CGLB_OK;
     size_t smem = sizeof(double) * (size_t)(m > 0 ? m : 1);
     CGLB_CUDA_OK(cudaFuncSetAttribute(gemv_cols_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
-    gemv_cols_finish_kernel<<<(unsigned)((ncols + 255) / 256), 128, smem, st>>>(a, m, ncols, lda, w_out, r, 1.0 / sigma_sq, z, rz_dev);
+    gemv_cols_finish_kernel<<<(unsigned)nfin, 128, smem, st>>>(a, m, ncols, lda, wpart, w_out, r, 1.0 / sigma_sq, z, rz_dev, rzpart,
+                                                                ctx->counters + 1);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;

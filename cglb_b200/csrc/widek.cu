@@ -19,7 +19,8 @@ constexpr int WT_THREADS = 256;
 struct WideArgs {
     const double* xp_rows; const double* xp_cols;   // wide packed [.][W]
     const double* vcol;                              // padded column vector
-    double* y;
+    double* y;                                       // CTA b accumulates into y + b * ystride (fixed order, kmv_impl.cuh)
+    long ystride;
     const double* exp_tab;
     long nrows, ncols;
     long nb_rows;            // row blocks of 128
@@ -78,6 +79,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_sweep_kernel(const WideArg
     uint32_t rowphase = 0;
     const double var = args.variance;
     const uint32_t tile_bytes = (uint32_t)(WT_COLS * W * sizeof(double));
+    // this CTA's copy of y: every add below follows a CTA barrier and column j / row i always belong to the same thread
+    double* const yb = args.y + (long)blockIdx.x * args.ystride;
 
     for (long tau = blockIdx.x;; tau += gridDim.x) {
         const long t = tau * args.nparts + args.part;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_sweep_kernel(const WideArg
                     const long j = j0 + tid;
                     const double* sc4 = s_col + (tile & 1) * 4 * WT_COLS;
                     const double s = sc4[tid] + sc4[WT_COLS + tid] + sc4[2 * WT_COLS + tid] + sc4[3 * WT_COLS + tid];
-                    if (j < args.ncols) atomicAdd(args.y + j, var * s);
+                    if (j < args.ncols) atomicAdd(yb + j, var * s);
                 }
             }
         }
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_sweep_kernel(const WideArg
         __syncthreads();
         if (tid < WT_ROWS) {
             const long row = r0 + tid;
-            if (row < args.nrows) atomicAdd(args.y + row, var * (s_row[tid] + s_row[WT_ROWS + tid]));
+            if (row < args.nrows) atomicAdd(yb + row, var * (s_row[tid] + s_row[WT_ROWS + tid]));
         }
     }
 }
@@ -233,9 +236,9 @@ static size_t wide_smem_bytes(int w) {
 }
 
 int wide_sweep(Context* ctx, int kind, bool sym, const double* xp_rows, long nrows, const double* xp_cols, long ncols, int d,
-               const double* vcol, double* y, double variance, int part, int nparts, cudaStream_t st) {
+               const double* vcol, double* y, long ystride, double variance, int part, int nparts, cudaStream_t st) {
     WideArgs a{};
-    a.xp_rows = xp_rows; a.xp_cols = xp_cols; a.vcol = vcol; a.y = y; a.exp_tab = ctx->exp_table;
+    a.xp_rows = xp_rows; a.xp_cols = xp_cols; a.vcol = vcol; a.y = y; a.ystride = ystride; a.exp_tab = ctx->exp_table;
     a.nrows = nrows; a.ncols = ncols; a.variance = variance; a.d = d; a.kp = wide_kp(d); a.w = packed_width(d);
     a.part = part; a.nparts = nparts;
     a.nb_rows = (nrows + WT_ROWS - 1) / WT_ROWS;
@@ -277,8 +280,9 @@ constexpr int WB_CP = 68;            // pitch of the c tile
 struct WideBwdArgs {
     const double* xp;                // wide packed [n_pad][W]
     const double* wcol; const double* ucol;   // padded vectors
-    double* rsum;                    // R (atomics)
-    double* gout;                    // [d+1]: -2 X_q, variance sum
+    double* rsum;                    // R: CTA b accumulates into rsum + b * ystride
+    double* gout;                    // [d+1]: -2 X_q, variance sum of CTA b at gout + b * gstride
+    long ystride, gstride;
     const double* exp_tab;
     long n;
     long nb_rows, n_chunks, nitems;
@@ -329,6 +333,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_bwd_kernel(const WideBwdAr
     uint32_t rowphase = 0;
     const uint32_t tile_bytes = (uint32_t)(WT_COLS * W * sizeof(double));
     double gvar = 0.0;
+    double* const rb = args.rsum + (long)blockIdx.x * args.ystride;
+    double* const gb = args.gout + (long)blockIdx.x * args.gstride;
+    double gx = 0.0;                 // thread tid < d: running -2 X_q of this CTA (items in their static order)
 
     auto issue_tile = [&](long j0) {
         mbar_wait(&s_empty[pstage], pphase ^ 1);
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_bwd_kernel(const WideBwdAr
             if (offdiag && tid < WT_COLS) {
                 const long j = j0 + tid;
                 const double* sc2 = s_col + (tile & 1) * 2 * WT_COLS;
-                if (j < args.n) atomicAdd(args.rsum + j, sc2[tid] + sc2[WT_COLS + tid]);
+                if (j < args.n) atomicAdd(rb + j, sc2[tid] + sc2[WT_COLS + tid]);
             }
             // ---- phase B: Y[rows of this warp (8)] += C[8 x 64] * A_J[64 x KP]
             {
@@ -496,22 +503,23 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wide_bwd_kernel(const WideBwdAr
         __syncthreads();
         if (tid < WB_ROWS) {
             const long row = r0 + tid;
-            if (row < args.n) atomicAdd(args.rsum + row, s_row[tid] + s_row[WB_ROWS + tid] + s_row[2 * WB_ROWS + tid] + s_row[3 * WB_ROWS + tid]);
+            if (row < args.n) atomicAdd(rb + row, s_row[tid] + s_row[WB_ROWS + tid] + s_row[2 * WB_ROWS + tid] + s_row[3 * WB_ROWS + tid]);
         }
         if (tid < args.d) {
             double s = 0.0;
 #pragma unroll
             for (int w8 = 0; w8 < 8; ++w8) s += s_xq[w8 * NQ * 8 + tid];
-            atomicAdd(args.gout + tid, -2.0 * s);
+            gx = fma(-2.0, s, gx);
         }
     }
+    if (tid < args.d) gb[tid] = gx;
     gvar = warp_sum(gvar);
     if (lane == 0) s_red[warp] = gvar;
     __syncthreads();
     if (tid == 0) {
         double s = 0.0;
         for (int w8 = 0; w8 < 8; ++w8) s += s_red[w8];
-        atomicAdd(args.gout + args.d, s);
+        gb[args.d] = s;
     }
 }
 
@@ -536,9 +544,10 @@ static int launch_wide_bwd(Context* ctx, const WideBwdArgs& a, int grid, cudaStr
 }
 
 int wide_bwd_sweep(Context* ctx, int kind, const double* xp, long n, int d, const double* wcol, const double* ucol, double* rsum,
-                   double* gout, int part, int nparts, cudaStream_t st) {
+                   long ystride, double* gout, long gstride, int part, int nparts, cudaStream_t st) {
     WideBwdArgs a{};
-    a.xp = xp; a.wcol = wcol; a.ucol = ucol; a.rsum = rsum; a.gout = gout; a.exp_tab = ctx->exp_table;
+    a.xp = xp; a.wcol = wcol; a.ucol = ucol; a.rsum = rsum; a.ystride = ystride; a.gout = gout; a.gstride = gstride;
+    a.exp_tab = ctx->exp_table;
     a.n = n; a.d = d; a.kp = wide_kp(d); a.w = packed_width(d); a.part = part; a.nparts = nparts;
     a.nb_rows = (n + WB_ROWS - 1) / WB_ROWS;
     a.n_chunks = (n + WT_CHUNK - 1) / WT_CHUNK;

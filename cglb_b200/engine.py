@@ -130,6 +130,20 @@ class Engine:
             self.stream()), "cglb_kmv_sym"))
         return out
 
+    def kmv_sym_multi(self, kind, xp, n, d, v, variance, diag, out=None, part=0, nparts=1) -> Tensor:
+        """Y = variance K(X,X) V + diag V for V of shape [n, t] (the reference's `A @ x`, x: [N, t])."""
+        _req(xp, "xp"); _req(v, "v")
+        if v.dim() != 2 or v.shape[0] != n:
+            raise CglbError(f"v: expected shape [{n}, t], got {tuple(v.shape)}")
+        t = int(v.shape[1])
+        if out is None:
+            out = self.empty(n, t)
+        _req(out, "out")
+        self._timed("kmv_sym_multi", lambda: check(self.lib.cglb_kmv_sym_multi(
+            self.ctx, KIND_IDS[kind], ptr(xp), n, d, ptr(v), t, ptr(out), float(variance), float(diag), int(part), int(nparts),
+            self.stream()), "cglb_kmv_sym_multi"))
+        return out
+
     # ---- fp32-pair mode (models created under set_default_float("fp32")) --------------------------------
     def pack_f32(self, kind: str, x: Tensor, lengthscale: Tensor, shift: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
         _req(x, "x"); _req(lengthscale, "lengthscale")

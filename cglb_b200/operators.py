@@ -110,6 +110,16 @@ class KernelOperator:
     def __matmul__(self, v: Tensor) -> Tensor:
         kind, ls, var = _kernel_pieces(self.kernel)
         if v.ndim == 2 and v.shape[1] != 1:
+            # x: [N, t] (conjugate_gradient.py:57,66,72).  Without a tape the block goes through the multi-RHS sweep (every
+            # kernel pair evaluated once for all t columns); with one, column by column through the differentiable node.
+            diag0 = self.diag_value if self.diag_value is not None else torch.zeros((), dtype=v.dtype, device=v.device)
+            taped = torch.is_grad_enabled() and not self.detached and (
+                ls.requires_grad or var.requires_grad or diag0.requires_grad or v.requires_grad)
+            n, d = self.x1.shape
+            if self.symmetric and not taped and d <= 32:
+                xp = self.packed(ls.detach().to(torch.float64).contiguous())
+                y = self.engine.kmv_sym_multi(kind, xp, n, d, v.detach().to(torch.float64).contiguous(), float(var), float(diag0))
+                return y.to(v.dtype)
             return torch.cat([self @ v[:, j:j + 1] for j in range(v.shape[1])], 1)
         if self.symmetric:
             diag = self.diag_value if self.diag_value is not None else torch.zeros((), dtype=v.dtype, device=v.device)

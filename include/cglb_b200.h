@@ -74,6 +74,15 @@ CGLB_API int cglb_pack_inputs(cglb_context* ctx, int kind, const double* x, long
 CGLB_API int cglb_kmv_sym(cglb_context* ctx, int kind, const double* xp, long n, int d, const double* v, double* y,
                  double variance, double diag, int part, int nparts, void* stream);
 
+/* The same product against a block of t right-hand sides: Y = variance * K(X,X) V + diag * V with V, Y [n][t] row-major
+ * (the layout of the reference's [N, t] tensors).  Columns are processed in groups of 4 (2 for a last pair); within a
+ * group every kernel pair is evaluated ONCE and used for all its accumulations (3d + 5 + 2t FLOPs per pair instead of
+ * t (3d + 7)).  d <= 32; t = 1 forwards to cglb_kmv_sym.  part / nparts as in cglb_kmv_sym.
+ * replaces: `A @ x` for x of shape [N, t] -- the operator protocol of cglb/backend/pytorch/conjugate_gradient.py:57,66,72
+ * ("b: [N, t]" in its docstring) and cglb/backend/pytorch/models.py:280. */
+CGLB_API int cglb_kmv_sym_multi(cglb_context* ctx, int kind, const double* xp, long n, int d, const double* v, int t, double* y,
+                       double variance, double diag, int part, int nparts, void* stream);
+
 /* Which kernel cglb_kmv_sym launches for this shape: 0 = register-resident DFMA sweep (kmv_impl.cuh),
  * 1 = DMMA-distance sweep for 10 <= d <= 32 (dsweep_impl.cuh), 2 = wide DMMA sweep for d > 32 (widek.cu).
  * Pure query (no launch); benchmarks use it to name the kernel they time. */

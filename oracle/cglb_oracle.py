@@ -282,6 +282,48 @@ def bound_and_grads(kind: str, p: OracleParams, x, y, v0, **kw):
     return loss.detach(), [g.detach() for g in grads], res
 
 
+def bound_and_grads_fixed_v_blocked(kind: str, p: OracleParams, x: Tensor, y: Tensor, v: Tensor, jitter: float = 1e-6,
+                                    block: int = 256):
+    """``bound_and_grads(..., use_cached_v=True)`` for n too large for a dense K with an autograd tape (the [n, n, d]
+    difference tensor of ``sqdist_direct``): the same statements of models.py:151-286 with ``cov @ v`` (models.py:280)
+    evaluated in row blocks.  Exact autograd in two stages: (1) ``Kv`` enters the bound as a leaf, one backward gives the
+    direct parameter gradients and g = d(loss)/d(Kv); (2) sum_blocks g_blk^T (K_blk(theta) v) is differentiated block by
+    block, so only one [block, n, d] tape is alive at a time.  Checked against the dense oracle in
+    tests/test_oracle_golden.py."""
+    n = x.shape[0]
+    nf = float(n)
+    v = v.detach().reshape(-1, 1)
+    sigma_sq_d = p.noise.detach()
+    with torch.no_grad():
+        rows = [kernel_dense(kind, x[i:i + block], x, p.lengthscale, p.variance) @ v for i in range(0, n, block)]
+        kv_val = torch.cat(rows, 0)
+    kv_leaf = kv_val.clone().requires_grad_(True)                                # variance K(X,X) v
+    terms = common_terms(kind, p, x, jitter)
+    logdet = logdet_term(p, x, terms)
+    sigma_sq = p.noise
+    cov_v = kv_leaf + sigma_sq * v                                               # :251-252, :280
+    err = y.reshape(-1, 1) - p.mean_constant.reshape(1, 1)                       # :253-254
+    precon = nystrom_preconditioner(terms.A, terms.LB, sigma_sq)
+    r = err - cov_v                                                              # :281
+    _, error_bound = precon(r)                                                   # :282
+    lower = (v * (r + 0.5 * cov_v)).sum()                                        # :283
+    upper = lower + 0.5 * error_bound                                            # :284
+    bound = -upper + logdet - 0.5 * nf * math.log(2.0 * math.pi)                 # :162-168
+    loss = -bound
+    params = p.tensors()
+    grads = list(torch.autograd.grad(loss, params + [kv_leaf]))
+    g_kv = grads.pop().detach()
+    grads = [g.detach().clone() for g in grads]
+    kparams = [p.raw_outputscale, p.raw_lengthscale]
+    for i in range(0, n, block):
+        f = (g_kv[i:i + block] * (kernel_dense(kind, x[i:i + block], x, p.lengthscale, p.variance) @ v)).sum()
+        go, gl = torch.autograd.grad(f, kparams)
+        grads[3] += go
+        grads[4] += gl
+    del sigma_sq_d
+    return loss.detach(), grads
+
+
 def predict(kind: str, p: OracleParams, x: Tensor, y: Tensor, xnew: Tensor, v0: Tensor,
             jitter: float = 1e-6, max_error: float = 1e-3):
     """PredictCG.forward, models.py:307-354 (tight CG, max_error=1e-3 at :291)."""

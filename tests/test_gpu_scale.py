@@ -17,7 +17,7 @@ def eng():
     return get_engine()
 
 
-@pytest.mark.parametrize("kind,n,d", [("rbf", 40000, 8), ("matern32", 434000, 3), ("matern32", 2000000, 11)])
+@pytest.mark.parametrize("kind,n,d", [("rbf", 40000, 8), ("matern32", 434000, 3), ("matern32", 515000, 90), ("matern32", 2000000, 11)])
 def test_full_size_matvec_properties(eng, kind, n, d):
     dev = eng.device
     g = torch.Generator(device=dev).manual_seed(0)

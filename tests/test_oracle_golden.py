@@ -147,3 +147,19 @@ def test_expanded_distance_matches_direct_form():
     a = o.sqdist_direct(x, x, p.lengthscale.detach())
     b = o.sqdist_expanded(x, x, p.lengthscale.detach(), x1_eq_x2=True)
     assert float((a - b).abs().max()) < 1e-12
+
+
+def test_blocked_fixed_v_oracle_matches_the_dense_one():
+    """oracle.bound_and_grads_fixed_v_blocked (used by the GPU tests at Nystrom sizes M = 1024 / 2048, n = 16k) against the
+    dense oracle on a problem small enough for both."""
+    n, d, M = 700, 5, 48
+    x, y, z = o.synthetic_problem(n, d, M, seed=17)
+    v = 0.1 * torch.randn(n, 1, dtype=f64, generator=torch.Generator().manual_seed(3))
+    for kind in ("matern32", "rbf"):
+        p = o.OracleParams.from_values(0.05, 0.1, z, 1.3, np.linspace(0.8, 1.4, d))
+        loss_d, grads_d, _ = o.bound_and_grads(kind, p, x, y, v, use_cached_v=True)
+        p2 = o.OracleParams.from_values(0.05, 0.1, z, 1.3, np.linspace(0.8, 1.4, d))
+        loss_b, grads_b = o.bound_and_grads_fixed_v_blocked(kind, p2, x, y, v, block=96)
+        assert abs(float(loss_d) - float(loss_b)) <= 1e-13 * abs(float(loss_d))
+        for a, b in zip(grads_d, grads_b):
+            assert _rel(b.numpy(), a.numpy()) <= 1e-11
