@@ -58,33 +58,38 @@ class ConjugateGradient:
             raise CglbError("ConjugateGradient needs CUDA tensors (cglb_b200 has no CPU fallback)")
         eng = get_engine(b.device)
         n = b.numel()
-        b = b.contiguous()
-        v = v.clone().contiguous()                                    # :55
-        Av = (A @ v).contiguous()                                     # :57
+        # the kernels are fp64 and take dense vectors: fp32 models (set_default_float("fp32")) and strided views are
+        # promoted here, the results are cast back to the caller's dtype below
+        out_dtype = b.dtype
+        b = b.to(torch.float64).contiguous()
+        v = v.to(torch.float64).clone().contiguous()                  # :55
+        Av = (A @ v).to(torch.float64).contiguous()                   # :57
         r = torch.empty_like(b)
         eng.residual(n, b, Av, r)                                     # :58
         z, rz = precond(r)                                            # :59
+        z = z.to(torch.float64).contiguous()
         p = z.clone()
-        rz = rz.reshape(1).clone()
+        rz = rz.to(torch.float64).reshape(1).clone()
         pAp = torch.empty_like(rz)
         rz_host = float(rz.item())
         i = 0
         while (0.5 * rz_host > self.max_error) and (i < self.max_cg_iter):        # :65
-            Ap = (A @ p).contiguous()                                 # :66
+            Ap = (A @ p).to(torch.float64).contiguous()               # :66
             eng.dot(p, Ap, pAp)
             restart = i % self.restart_cg_iter == self.restart_cg_iter - 1         # :70
             eng.cg_step(n, rz, pAp, p, Ap, v, r, restart)             # :67-68, :72 (non-restart branch)
             if restart:
-                Av = (A @ v).contiguous()
+                Av = (A @ v).to(torch.float64).contiguous()
                 eng.residual(n, b, Av, r)                             # :72 (restart branch)
             z, new_rz = precond(r)                                    # :73
-            new_rz = new_rz.reshape(1)
-            eng.cg_direction(n, z.contiguous(), p, new_rz, rz, restart)             # :75
+            new_rz = new_rz.to(torch.float64).reshape(1)
+            z = z.to(torch.float64).contiguous()
+            eng.cg_direction(n, z, p, new_rz, rz, restart)            # :75
             rz = new_rz.clone()
             rz_host = float(rz.item())                                # the loop test is evaluated on the host, as in :65
             i += 1
-        stats = ConjugateGradientStats(i, torch.tensor(0.5 * rz_host, dtype=b.dtype))   # :83
-        return v, stats, ConjugateGradientState(r=r, z=z, rz=rz)
+        stats = ConjugateGradientStats(i, torch.tensor(0.5 * rz_host, dtype=out_dtype))   # :83
+        return v.to(out_dtype), stats, ConjugateGradientState(r=r, z=z, rz=rz)
 
 
 @dataclass
@@ -104,11 +109,14 @@ class NystromPreconditioner:
     def __post_init__(self):
         if not self.A.is_cuda:
             raise CglbError("NystromPreconditioner needs CUDA tensors (cglb_b200 has no CPU fallback)")
+        self._out_dtype = self.A.dtype
+        if self.A.dtype != torch.float64:         # fp32 models: the GEMV pair streams an fp64 copy
+            self.A = self.A.to(torch.float64)
         if self.A.stride(-1) != 1:
             self.A = self.A.contiguous()          # e.g. a column-major result of a triangular solve
         self._eng = get_engine(self.A.device)
         if self.lbinv is None:
-            self.lbinv = self._eng.tri_inverse(self.LB.detach().contiguous())
+            self.lbinv = self._eng.tri_inverse(self.LB.detach().to(torch.float64).contiguous())
         self._m = self.A.shape[0]
         self._sigma_sq = float(self.sigma_sq)
         if self.shard is None:
@@ -118,7 +126,7 @@ class NystromPreconditioner:
 
     def __call__(self, r: Tensor) -> Tuple[Tensor, Tensor]:
         eng, m = self._eng, self._m
-        rf = r.detach().reshape(-1)
+        rf = r.detach().reshape(-1).to(torch.float64).contiguous()
         n = rf.numel()
         lo, hi = self.cols if self.cols is not None else (0, n)
         ncols = hi - lo
@@ -130,6 +138,8 @@ class NystromPreconditioner:
         eng.precond_finish(self.A, m, ncols, self.lbinv, self._q, r_loc, self._sigma_sq,
                            zbuf[lo:hi], self._w, zbuf[n:])                        # :106-113
         self.shard.all_reduce(zbuf)
+        if self._out_dtype != torch.float64 and r.dtype != torch.float64:
+            return zbuf[:n].reshape(r.shape).to(r.dtype), zbuf[n].to(r.dtype)
         return zbuf[:n].reshape(r.shape), zbuf[n]
 
     @property

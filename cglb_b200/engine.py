@@ -47,6 +47,17 @@ def _req(t: Tensor, name: str, dtype=torch.float64):
     return t
 
 
+def _req2d(t: Tensor, name: str):
+    """a row-major matrix (or a column slice of one): fp64, CUDA, unit stride along the rows"""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise CglbError(f"{name}: expected a CUDA tensor (cglb_b200 has no CPU fallback)")
+    if t.dtype != torch.float64:
+        raise CglbError(f"{name}: expected dtype torch.float64, got {t.dtype}")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise CglbError(f"{name}: expected a row-major 2-D tensor")
+    return t
+
+
 class Engine:
     def __init__(self, device_index: int):
         self.lib = _ffi.load_library()
@@ -240,29 +251,40 @@ class Engine:
 
     # ---- K3 / K4 --------------------------------------------------------------------------------------
     def precond_project(self, a: Tensor, m: int, ncols: int, r: Tensor, q: Tensor) -> Tensor:
+        _req2d(a, "a"); _req(r, "r"); _req(q, "q")
         self._timed("precond_project", lambda: check(self.lib.cglb_precond_project(
             self.ctx, ptr(a), m, ncols, a.stride(0), ptr(r), ptr(q), self.stream()), "cglb_precond_project"))
         return q
 
     def precond_finish(self, a: Tensor, m: int, ncols: int, lbinv: Tensor, q: Tensor, r: Tensor, sigma_sq: float,
                        z: Tensor, w: Tensor, rz: Tensor):
+        _req2d(a, "a"); _req(lbinv, "lbinv"); _req(q, "q"); _req(r, "r"); _req(z, "z"); _req(w, "w"); _req(rz, "rz")
         self._timed("precond_finish", lambda: check(self.lib.cglb_precond_finish(
             self.ctx, ptr(a), m, ncols, a.stride(0), ptr(lbinv), ptr(q), ptr(r), float(sigma_sq), ptr(z), ptr(w), ptr(rz),
             self.stream()), "cglb_precond_finish"))
 
     # ---- K8 -------------------------------------------------------------------------------------------
     def dot(self, x: Tensor, y: Tensor, out: Tensor) -> Tensor:
+        _req(x, "x"); _req(y, "y"); _req(out, "out")
+        if x.numel() != y.numel():
+            raise CglbError("dot: operands differ in length")
         check(self.lib.cglb_dot(self.ctx, ptr(x), ptr(y), x.numel(), ptr(out), self.stream()), "cglb_dot")
         return out
 
     def cg_step(self, n, rz, pAp, p, Ap, v, r, restart: bool):
+        for name, t in (("rz", rz), ("pAp", pAp), ("p", p), ("Ap", Ap), ("v", v), ("r", r)):
+            _req(t, name)
         check(self.lib.cglb_cg_step(self.ctx, n, ptr(rz), ptr(pAp), ptr(p), ptr(Ap), ptr(v), ptr(r), int(restart), self.stream()), "cglb_cg_step")
 
     def residual(self, n, b, Av, r):
+        _req(b, "b"); _req(Av, "Av"); _req(r, "r")
         check(self.lib.cglb_residual(self.ctx, n, ptr(b), ptr(Av), ptr(r), self.stream()), "cglb_residual")
 
     def cg_direction(self, n, z, p, rz_new, rz_old, restart: bool):
+        _req(z, "z"); _req(p, "p"); _req(rz_new, "rz_new"); _req(rz_old, "rz_old")
         check(self.lib.cglb_cg_direction(self.ctx, n, ptr(z), ptr(p), ptr(rz_new), ptr(rz_old), int(restart), self.stream()), "cglb_cg_direction")
 
     def quad_terms(self, n, err, Kv, v, r, out):
+        for name, t in (("err", err), ("Kv", Kv), ("v", v), ("r", r), ("out", out)):
+            _req(t, name)
         check(self.lib.cglb_quad_terms(self.ctx, n, ptr(err), ptr(Kv), ptr(v), ptr(r), ptr(out), self.stream()), "cglb_quad_terms")

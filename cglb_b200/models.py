@@ -218,7 +218,8 @@ class LowerBoundCG(nn.Module):
     def logdet_and_quad_common_terms(self, data: Tuple) -> CommonTerms:                   # models.py:176-213
         ev = self.evaluator(data)
         kind, ls, var = _kernel_pieces(self.kernel)
-        t = ev.common_terms(kind, self.inducing_points.detach(), ls.detach().reshape(-1).contiguous(), float(var),
+        t = ev.common_terms(kind, self.inducing_points.detach().to(torch.float64),
+                            ls.detach().reshape(-1).to(torch.float64).contiguous(), float(var),
                             float(self.noise), settings.cholesky_jitter.value())
         return CommonTerms(A=t.A[:, :t.ncols], LB=t.LB, AAt_diag_sum=t.AAt_diag_sum, L=t.L)
 
@@ -264,11 +265,15 @@ class PredictCG(LowerBoundCG):
         if full_cov:
             raise NotImplementedError("The predict_f method currently  supports only `full_cov=False` option")
         x, *_ = self.model.train_inputs
-        y = self.model.train_targets.reshape(-1, 1)
+        out_dtype = xnew.dtype
+        f64 = torch.float64
+        # fp32 models (set_default_float("fp32")): every operand is promoted, as LowerBoundCG._evaluate does, and the
+        # results are cast back (the kernels are fp64)
+        y = self.model.train_targets.reshape(-1, 1).to(f64)
         ev = self.evaluator((x, self.model.train_targets))
         eng = ev.eng
         kind, ls, var = _kernel_pieces(self.kernel)
-        ls = ls.detach().reshape(-1).contiguous()
+        ls = ls.detach().reshape(-1).to(f64).contiguous()
         var_f, noise = float(var), float(self.noise)
         mean_c = float(self.mean.constant.detach().reshape(-1)[0])
         err = (y - mean_c).contiguous()
@@ -276,19 +281,20 @@ class PredictCG(LowerBoundCG):
             terms = self.terms
             ev.pack(kind, ls)
         else:
-            terms = ev.common_terms(kind, self.inducing_points.detach(), ls, var_f, noise, settings.cholesky_jitter.value())
+            terms = ev.common_terms(kind, self.inducing_points.detach().to(f64), ls, var_f, noise, settings.cholesky_jitter.value())
         cov = ev.operator(kind, var_f, noise)
         precon = ev.preconditioner(terms, noise)
         if self.cached:
-            new_v = self.v_vec
+            new_v = self.v_vec.to(f64)
         else:
-            new_v, cg_stats = self.cg_opt(cov, err, self.v_vec, precon)                  # :330
+            new_v, cg_stats = self.cg_opt(cov, err, self.v_vec.to(f64), precon)          # :330
             self.v_vec.data.copy_(new_v)
             self.terms = terms
             self.cached = True
+        xnew = xnew.detach().to(f64).contiguous()
         nnew, d = xnew.shape
         m = terms.L.shape[0]
-        xnew_p = eng.pack(kind, xnew.detach().contiguous(), ls, ev.shift)
+        xnew_p = eng.pack(kind, xnew, ls, ev.shift)
         cg_mean = eng.kmv_rect(kind, xnew_p, nnew, ev.xp, ev.n, d, new_v.reshape(-1).contiguous(), var_f).reshape(-1, 1)   # :334
         res = err - cov @ new_v                                                          # :335
         # a_res = A @ res : this rank's columns, all-reduced                             # :340
@@ -308,7 +314,7 @@ class PredictCG(LowerBoundCG):
         sgpr_mean = (tmp2v.t() @ c).reshape(-1, 1)                                       # :347
         f_mean = sgpr_mean + cg_mean + mean_c                                            # :348
         f_var = var_f + (tmp2v ** 2).sum(0) - (tmp1v ** 2).sum(0)                        # :350-351
-        return f_mean, f_var.reshape(*f_mean.shape)
+        return f_mean.to(out_dtype), f_var.reshape(*f_mean.shape).to(out_dtype)
 
 
 def log_density(m, y, f_mean, f_var) -> Tensor:          # models.py:370-372

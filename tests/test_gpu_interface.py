@@ -92,6 +92,48 @@ def test_fp32_models_use_fp32_pair_sweeps(fp64_default):
         interface.set_default_float("fp64")
 
 
+def test_fp32_models_predict_and_metrics(fp64_default, tmp_path):
+    """an fp32 model must get through PredictCG, the sub-step methods and the Logger's metrics callback
+    (interface.py:607-658) -- every operand is promoted to the fp64 kernels and the results come back as fp32."""
+    interface.set_default_float("fp32")
+    try:
+        train, test = _data(n=400)
+        cfg = cb.CGLBConfig(kernel=cb.Matern32Config(), inducing_variable=cb.InducingVariableConfig(16))
+        model = cb.B200.create_model(cfg, train)
+        assert model.train_inputs[0].dtype == torch.float32
+        mean, var = cb.PredictCG(model)(torch.as_tensor(test[0], dtype=torch.float32).cuda())
+        assert mean.dtype == torch.float32 and var.dtype == torch.float32 and mean.shape == (100, 1)
+        assert torch.isfinite(mean).all() and (var > 0).all()
+        # the same prediction from an fp64 copy of the model: fp32 kernel pairs cost ~1e-6 per entry
+        interface.set_default_float("fp64")
+        model64 = cb.B200.create_model(cfg, train)
+        mean64, var64 = cb.PredictCG(model64)(torch.as_tensor(test[0], dtype=torch.float64).cuda())
+        assert float((mean.double() - mean64).abs().max()) <= 1e-3 * float(mean64.abs().max()) + 1e-4
+        assert float((var.double() - var64).abs().max()) <= 1e-3 * float(var64.abs().max())
+        interface.set_default_float("fp32")
+        lb = cb.LowerBoundCG(model)
+        terms = lb.logdet_and_quad_common_terms((model.train_inputs[0], model.train_targets))
+        assert terms.LB.shape == (16, 16)
+        m = cb.B200.metrics_fn(model, (train, test))()
+        assert np.isfinite(m["test/rmse"]) and np.isfinite(m["test/nlpd"]) and np.isfinite(m["loss"])
+        # the solver API called directly with fp32 / strided tensors: promoted, not misread
+        xd = model.train_inputs[0]
+        kern = model.covar_module.base_kernel
+        cov = kern(xd).add_diag(model.likelihood.noise.squeeze()).detach()
+        b = torch.randn(400, 2, dtype=torch.float32, device=xd.device)[:, :1]          # strided fp32 view
+        A = torch.randn(8, 400, dtype=torch.float32, device=xd.device) * 0.1
+        LB = torch.linalg.cholesky(torch.eye(8, device=xd.device) + A @ A.t())
+        pre = cb.NystromPreconditioner(A, LB, torch.tensor(1.0, device=xd.device))
+        v, st = cb.ConjugateGradient()(cov, b, torch.zeros_like(b), pre)
+        assert v.dtype == torch.float32 and torch.isfinite(v).all() and int(st.steps) >= 0
+        from cglb_b200.engine import get_engine
+        eng = get_engine()
+        with pytest.raises(cb.CglbError):
+            eng.dot(b.reshape(-1).contiguous(), b.reshape(-1).contiguous(), eng.empty(1))      # fp32 handed to an fp64 kernel
+    finally:
+        interface.set_default_float("fp64")
+
+
 def test_readme_command_shim(tmp_path):
     """README command of the reference (README.md:35) through the CLI shim, on a small synthetic dataset."""
     from click.testing import CliRunner
