@@ -32,6 +32,8 @@ namespace cglb {
 
 constexpr int DS_STAGES = 8;                  // 64-column tiles in the ring (4 in flight ahead of warp 0)
 constexpr int DS_RPC = 4;                     // row blocks per column chunk (chunk = 4 x rows per item)
+// forward sweep: packed widths whose 8-stage ring leaves room for TWO slabs of per-warp column sums (split-phase hand-over)
+__host__ __device__ constexpr bool DS_SPLIT(int dp) { return dp <= 16; }
 
 __device__ __forceinline__ void dmma884c(double (&d)[2], double a, double b, double c0, double c1) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
@@ -86,18 +88,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepAr
     constexpr int WROWS = 8 * MT;       // rows per warp
     using Cur = DCursor<DS_ROWS>;
     static_assert(DP % 2 == 0 && DP >= 4, "packed row width");
+    static_assert(DS_THREADS == DS_ROWS, "thread t adds row r0 + t and the columns c0 + t + 256 k of its CTA's copy");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_tab[kExpTabBig];                                  // static: LDS with an immediate base
     double* s_x = reinterpret_cast<double*>(smem_raw);                    // [DS_STAGES][kBJ*DP]
     double* s_v = s_x + DS_STAGES * kBJ * DP;                               // [DS_STAGES][kBJ]
-    double* s_slab = s_v + DS_STAGES * kBJ;                                 // [WARPS][chunk]: per-warp column sums of one item
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_slab + WARPS * Cur::DS_CHUNK);
+    // Fixed summation order (no run-to-run differences): inside an item every warp parks its column sums in its own row
+    // of a slab and its row sums in s_rsum; once all warps have done so the sums are added -- columns over the warps in
+    // warp order -- to THIS CTA's copy of y (args.y + blockIdx.x * ystride), the copies are summed in CTA order by a second
+    // kernel.  Address X of the copy is only ever touched by thread X % 256 (row blocks and chunk starts are multiples of
+    // 256), in the static order of the CTA's items.
+    // SPLIT (the widths whose ring leaves room for two slabs): the hand-over is split-phase.  A warp ARRIVES on s_item when
+    // its sums of item k are parked and goes on to item k + 1 (other slab); it waits for that phase only after it has issued
+    // the global loads of the next item's row fragments, and then adds its share of item k.  No warp waits at a barrier with
+    // nothing to do (a CTA barrier at every item end cost 2.2 % at d = 11).
+    constexpr bool SPLIT = DS_SPLIT(DP);
+    constexpr int NSLAB = SPLIT ? 2 : 1;
+    double* s_slab = s_v + DS_STAGES * kBJ;                                 // [NSLAB][WARPS][chunk] per-warp column sums
+    double* s_rsum = s_slab + NSLAB * WARPS * Cur::DS_CHUNK;                // [NSLAB][DS_ROWS] row sums
+    long* s_desc = reinterpret_cast<long*>(s_rsum + NSLAB * DS_ROWS);       // [NSLAB][4]: r0, c0, ntiles of the parked item
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_desc + NSLAB * 4);
     uint64_t* s_empty = s_full + DS_STAGES;
-    // Fixed summation order (no run-to-run differences): inside an item every warp parks its column sums in its own
-    // slab row; at the end of the item they are summed over the warps in warp order and added to THIS CTA's copy of y
-    // (args.y + blockIdx.x * ystride).  Two adds to one address come from the same thread (column j -> thread j % 256,
-    // row i -> its owner lane) or are separated by the CTA barriers at the end of an item; the copies are summed in CTA
-    // order by a second kernel.
+    uint64_t* s_item = s_empty + DS_STAGES;                                 // [1] arrivals: one per warp and item
     double* const yb = args.y + (long)blockIdx.x * args.ystride;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -110,6 +122,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepAr
     }
     if (tid == 0) {
         for (int s = 0; s < DS_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], DS_WARPS); }
+        mbar_init(s_item, DS_WARPS);
         mbar_fence_init();
     }
     __syncthreads();
@@ -136,6 +149,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepAr
         for (int i = 0; i < DS_STAGES / 2; ++i) produce(pc);
     }
     const double var = args.variance;
+    int item = 0;                 // items this CTA has parked so far (slab / phase = item & 1)
+    // adds the parked sums of item `it` (slab it & 1): every thread its own columns and its own row
+    auto add_parked = [&](int it) {
+        const int b = SPLIT ? (it & 1) : 0;
+        const long* dsc = s_desc + b * 4;
+        const long p_r0 = dsc[0], p_c0 = dsc[1];
+        const int p_ncols = (int)dsc[2] * kBJ;
+        const double* slab = s_slab + b * WARPS * Cur::DS_CHUNK;
+        for (int col = tid; col < p_ncols; col += DS_THREADS) {
+            const long jc = p_c0 + col;
+            if (p_c0 + (col & ~(kBJ - 1)) >= p_r0 + DS_ROWS && jc < args.ncols) {      // tiles beyond the row block only
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) s += slab[w * Cur::DS_CHUNK + col];
+                atomicAdd(yb + jc, var * s);
+            }
+        }
+        if (p_r0 + tid < args.nrows) atomicAdd(yb + p_r0 + tid, var * s_rsum[b * DS_ROWS + tid]);
+    };
 
     while (cc.valid) {
         const long r0 = cc.r0;
@@ -171,6 +203,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepAr
                 for (int ks = 1; ks < KS; ++ks) dmma884c(acc[i], af[i][ks], bf[ks], acc[i][0], acc[i][1]);
             }
         };
+        if (SPLIT && item > 0) {
+            // the row fragments above are in flight: now wait for every warp to have parked the previous item, add it
+            mbar_wait(s_item, (uint32_t)((item - 1) & 1));
+            add_parked(item - 1);
+        }
         // Software pipeline over n-tiles, across tile boundaries: the DMMAs of n-tile t+1 are issued before the
         // kernel map of n-tile t, so the map always has all 2 MT chains of a full n-tile to interleave.
         if (tid == 0) produce(pc);
@@ -233,7 +270,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepAr
                     const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // = 2 j + e
                     // every lane now holds one of the 32 column sums of this half tile (over the warp's rows): one
                     // conflict-free 256-byte store into the warp's slab row, no CTA barrier inside the item
-                    s_slab[warp * Cur::DS_CHUNK + tile * kBJ + half * 32 + (idx >> 1) * 8 + 2 * t4 + (idx & 1)] = c8[0];
+                    s_slab[((SPLIT ? (item & 1) : 0) * WARPS + warp) * Cur::DS_CHUNK + tile * kBJ + half * 32 + (idx >> 1) * 8 + 2 * t4 +
+                           (idx & 1)] = c8[0];
                 }
             }
             // this warp is done with the stage (the first n-tile of the next stage has been read already)
@@ -242,33 +280,40 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dmma_sweep_kernel(const SweepAr
             stage = nstage;
             phase = nphase;
         }
-        // item end: column sums of the tiles beyond the row block, summed over the warps in warp order
-        __syncthreads();
-        for (int col = tid; col < ntiles * kBJ; col += DS_THREADS) {
-            const long jc = c0 + col;
-            if (c0 + (col & ~(kBJ - 1)) >= r0 + DS_ROWS && jc < args.ncols) {
-                double s = 0.0;
+        // item end: park the row sums (over the 4 lanes sharing g; every warp owns its 32 rows) and the item's coordinates
+        {
+            const int b = SPLIT ? (item & 1) : 0;
 #pragma unroll
-                for (int w = 0; w < WARPS; ++w) s += s_slab[w * Cur::DS_CHUNK + col];
-                atomicAdd(yb + jc, var * s);
+            for (int i = 0; i < MT; ++i) {
+                double s = racc[i];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (t4 == 0) s_rsum[b * DS_ROWS + warp * WROWS + i * 8 + g] = s;
             }
+            if (tid == 0) { s_desc[b * 4] = r0; s_desc[b * 4 + 1] = c0; s_desc[b * 4 + 2] = ntiles; }
         }
-        // row sums: reduce over the 4 lanes sharing g; every warp owns its 32 rows
-#pragma unroll
-        for (int i = 0; i < MT; ++i) {
-            double s = racc[i];
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (t4 == 0 && live[i]) atomicAdd(yb + r0 + warp * WROWS + i * 8 + g, var * s);
+        if (SPLIT) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_item);       // release: this warp's sums of the item are visible to whoever waits
+        } else {
+            __syncthreads();
+            add_parked(item);
+            __syncthreads();                          // the slab is free again
         }
-        __syncthreads();      // the slab is free again; this item's adds precede the next item's
+        ++item;
         cc.tau += gridDim.x;
         cc.load_item(args, n_chunks);
     }
+    if (SPLIT && item > 0) {
+        mbar_wait(s_item, (uint32_t)((item - 1) & 1));
+        add_parked(item - 1);
+    }
 }
 
-static inline size_t dsweep_smem_bytes(int dp, int warps, int chunk) {
-    return (size_t)(DS_STAGES * kBJ * dp + DS_STAGES * kBJ + warps * chunk) * sizeof(double) + 2 * DS_STAGES * sizeof(uint64_t);
+static inline size_t dsweep_smem_bytes(int dp, int warps, int chunk, int rows) {
+    const int nslab = DS_SPLIT(dp) ? 2 : 1;
+    return (size_t)(DS_STAGES * kBJ * dp + DS_STAGES * kBJ + nslab * (warps * chunk + rows + 4)) * sizeof(double) +
+           (2 * DS_STAGES + 1) * sizeof(uint64_t);
 }
 
 template <int KIND, int DP, int WARPS = 8, int MT = 4>
@@ -279,7 +324,7 @@ static int run_dsweep(Context* ctx, SweepArgs a, cudaStream_t st) {
     a.nb_cols = n_chunks;
     a.nitems = DS_RPC * n_chunks * (n_chunks + 1) / 2;
     auto kern = dmma_sweep_kernel<KIND, DP, WARPS, MT>;
-    const size_t smem = dsweep_smem_bytes(DP, WARPS, CHUNK);
+    const size_t smem = dsweep_smem_bytes(DP, WARPS, CHUNK, ROWS);
     CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long my_items = (a.nitems - a.part + a.nparts - 1) / a.nparts;
     if (my_items <= 0) return CGLB_OK;
