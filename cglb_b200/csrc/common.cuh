@@ -58,7 +58,8 @@ struct Context {
     // output vector (ypart + blockIdx.x * stride), a second kernel sums the copies in CTA order
     double* ypart;        // [ypart_cap]
     long ypart_cap;
-    double* exp_table;    // [64] 2^(j/64) followed by [1024] 2^(j/1024); staged into shared memory by the kernels
+    double* exp_table;    // [64] 2^(j/64) followed by [1024] 2^(j/1024) with j << 10 subtracted from the high word
+                          // (fast_exp_neg<10>); staged into shared memory by the kernels
     unsigned long long launches;   // number of kernels this context launched (bench.py gpu_launches)
 };
 
@@ -179,6 +180,15 @@ __device__ __forceinline__ double fast_exp_neg(double s, const double* __restric
         p = fma(p, r, 1.0);
     }
     double T = tab[n & ((1 << TB) - 1)];
+    if (TB == 10) {
+        // The big table stores 2^(j/1024) with j << 10 SUBTRACTED from the high word (context.cu), so that one IMAD
+        // n * 2^10 + hi(T') = hi(2^(j/1024)) + ((n >> 10) << 20) forms 2^(n/1024) without masking n first (n = (n >> 10) 2^10
+        // + j): one LOP3 less per kernel pair.  Scaling by a power of two commutes with the rounding of the product, so the
+        // result has the same bits as "multiply, then insert the exponent".
+        int hi;
+        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(n), "n"(1 << (20 - TB)), "r"(__double2hiint(T)));
+        return __hiloint2double(hi, __double2loint(T)) * fma(r, p, 1.0);
+    }
     double res = T * fma(r, p, 1.0);
     int hi;      // hi(res) + ((n >> TB) << 20)
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(n & ~((1 << TB) - 1)), "n"(1 << (20 - TB)), "r"(__double2hiint(res)));

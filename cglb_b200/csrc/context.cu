@@ -94,7 +94,14 @@ extern "C" int cglb_create(cglb_context** out, int device) {
     CGLB_CUDA_OK(cudaMemset(ctx->counters, 0, sizeof(int) * 16));
     static double tab[kExpTabSmall + kExpTabBig];
     for (int j = 0; j < kExpTabSmall; ++j) tab[j] = exp2((double)j / kExpTabSmall);
-    for (int j = 0; j < kExpTabBig; ++j) tab[kExpTabSmall + j] = exp2((double)j / kExpTabBig);
+    for (int j = 0; j < kExpTabBig; ++j) {
+        // fast_exp_neg<10> adds n * 2^10 = ((n >> 10) << 20) + (j << 10) to the high word: pre-subtract j << 10
+        const double t = exp2((double)j / kExpTabBig);
+        unsigned long long bits;
+        memcpy(&bits, &t, sizeof(bits));
+        bits -= (unsigned long long)j << 42;
+        memcpy(&tab[kExpTabSmall + j], &bits, sizeof(bits));
+    }
     CGLB_CUDA_OK(cudaMalloc(&ctx->exp_table, sizeof(tab)));
     CGLB_CUDA_OK(cudaMemcpy(ctx->exp_table, tab, sizeof(tab), cudaMemcpyHostToDevice));
     *out = reinterpret_cast<cglb_context*>(ctx);
