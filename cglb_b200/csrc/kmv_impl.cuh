@@ -521,6 +521,9 @@ struct KnmArgs {
     double* out_ls;                    // [D]   accumulated
     double* out_var;                   // [1]   accumulated
     double* out_z;                     // [m][D] accumulated
+    // backward, fixed summation order: CTA (bx, by) stores its sums (plain stores), knm_bwd_reduce_kernel adds them in bx order
+    double* zpart;                     // [gridDim.x][m][D]
+    double* lspart;                    // [gridDim.y][gridDim.x][D + 1]
     double cscale;                     // sqrt3 (Matern32) or 1/sqrt2 (RBF): packed = cscale * (x - shift) / l
     double cfac;                       // 1 (Matern32) or 2 (RBF)
 };
@@ -639,7 +642,7 @@ __global__ void __launch_bounds__(256) knm_bwd_kernel(const KnmArgs args) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) s += s_part[w][mm][k];
-        if (args.out_z) atomicAdd(args.out_z + (m0 + mm) * D + k, -args.cscale / args.lengthscale[k] * s);
+        if (args.out_z) args.zpart[((long)blockIdx.x * args.m + m0 + mm) * D + k] = -args.cscale / args.lengthscale[k] * s;
     }
     // lengthscale / variance sums: block reduce, one atomic per CTA per component
 #pragma unroll
@@ -655,18 +658,51 @@ __global__ void __launch_bounds__(256) knm_bwd_kernel(const KnmArgs args) {
     if (tid <= D) {
         double s = 0.0;
         for (int w = 0; w < 8; ++w) s += s_red[w][tid];
-        if (tid < D) atomicAdd(args.out_ls + tid, s / args.lengthscale[tid]);
-        else atomicAdd(args.out_var, s);
+        args.lspart[((long)blockIdx.y * gridDim.x + blockIdx.x) * (D + 1) + tid] = (tid < D) ? s / args.lengthscale[tid] : s;
+    }
+}
+
+// second stage of the K_nm backward: out_z[i] += sum_bx zpart[bx][i]; out_ls / out_var += sum over the CTAs in (by, bx) order
+static __global__ void knm_bwd_reduce_kernel(const double* __restrict__ zpart, long gx, long md, double* __restrict__ out_z,
+                                      const double* __restrict__ lspart, long nctas, int d, double* __restrict__ out_ls,
+                                      double* __restrict__ out_var) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (out_z != nullptr && i < md) {
+        double s = 0.0;
+#pragma unroll 8
+        for (long b = 0; b < gx; ++b) s += zpart[b * md + i];
+        out_z[i] += s;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x <= d) {
+        double s = 0.0;
+        for (long b = 0; b < nctas; ++b) s += lspart[b * (d + 1) + threadIdx.x];
+        if ((int)threadIdx.x < d) out_ls[threadIdx.x] += s;
+        else *out_var += s;
     }
 }
 
 template <int KIND, int D>
-static int run_knm(Context* ctx, int bwd, const KnmArgs& a, cudaStream_t st) {
+static int run_knm(Context* ctx, int bwd, KnmArgs a, cudaStream_t st) {
     if (a.m <= 0 || a.ncols <= 0) return CGLB_OK;
     const int rows = bwd ? knm_bwd_rows(D) : kKnmRows;
     dim3 grid((unsigned)((a.ncols + 255) / 256), (unsigned)((a.m + rows - 1) / rows));
-    if (bwd) knm_bwd_kernel<KIND, D><<<grid, 256, 0, st>>>(a);
-    else knm_build_kernel<KIND, D><<<grid, 256, 0, st>>>(a);
+    if (!bwd) {
+        knm_build_kernel<KIND, D><<<grid, 256, 0, st>>>(a);
+        ctx->launches++;
+        CGLB_LAUNCH_OK();
+        return CGLB_OK;
+    }
+    const long md = a.m * D, nctas = (long)grid.x * grid.y;
+    const long zwords = a.out_z ? (long)grid.x * md : 0;
+    int rc = ensure_ypart(ctx, zwords + nctas * (D + 1));
+    if (rc) return rc;
+    a.zpart = ctx->ypart;
+    a.lspart = ctx->ypart + zwords;
+    knm_bwd_kernel<KIND, D><<<grid, 256, 0, st>>>(a);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
+    const long work = a.out_z ? md : 1;
+    knm_bwd_reduce_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(a.zpart, grid.x, md, a.out_z, a.lspart, nctas, D, a.out_ls, a.out_var);
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;

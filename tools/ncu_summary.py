@@ -28,11 +28,16 @@ def main():
     for path in sys.argv[1:]:
         rows = list(csv.reader(open(path)))
         h, u = rows[0], rows[1]
+        seen = {}
         for r in rows[2:]:
             name = r[h.index("Kernel Name")]
             if r[h.index("gpu__time_duration.sum")] in ("", "nan", "-nan") or "nan" in r[h.index("smsp__inst_executed.sum")]:
                 continue
-            print(f"## `{name}`  ({path.split('/')[-1]})\n")
+            grid = r[h.index("Grid Size")] if "Grid Size" in h else ""
+            seen[(name, grid)] = seen.get((name, grid), 0) + 1
+            if seen[(name, grid)] > 1:          # repeated launches of one kernel with one grid: the first stands for all
+                continue
+            print(f"## `{name}`  grid {grid}  ({path.split('/')[-1]})\n")
             print("| counter | value |\n|---|---|")
             for k, label in KEYS:
                 if k in h:
