@@ -10,6 +10,8 @@
 // (cuSOLVER dpotrf, cuBLAS dtrsm/dgemm).  FP64 has no tcgen05 form; mma.sync.m8n8k4.f64 (DMMA) measured
 // 37.1 TFLOP/s on this B200 vs 34.2 for plain DFMA (profiles/fp64_peaks_r01.json), so the contraction
 // runs on DMMA.
+#include <type_traits>
+
 #include "kmv_impl.cuh"
 
 namespace cglb {
@@ -81,9 +83,137 @@ struct GemmSmem {
     static constexpr size_t bytes = (size_t)GSTAGES * (kA + kB) * sizeof(double);
 };
 
+// Epilogue shared by the two GEMM kernels: lane (g, t) of warp (wm, wn) holds rows wm*64 + 8i + g, columns wn*32 + 8j + 2t + e
+// of the 128 x 128 tile (bm, bn).  `active` is false for threads that only take part in the CTA barriers (the TMA producer warp).
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue(const GemmArgs& p, double (&acc)[8][4][2], int bm, int bn, int tid, bool active) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 2) & 1, wn = warp & 3;
+    const long m0 = (long)bm * GM, n0 = (long)bn * GN;
+    if (EPI == EPI_KMAP || EPI == EPI_KBWD) {
+        __shared__ double s_tab[64];
+        __syncthreads();
+        if (tid < 64) s_tab[tid] = p.ke.exp_tab[tid];
+        __syncthreads();
+        if (!active) return;
+        double gk = 0.0, racc[8], cacc[4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) racc[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cacc[j][0] = cacc[j][1] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long row = m0 + wm * 64 + i * 8 + g;
+            const bool rlive = row < p.m;
+            const double nzr = rlive ? p.ke.nz[row * p.ke.nz_stride] : 0.0;
+            const double wtr = (EPI == EPI_KBWD && rlive && p.ke.wt) ? p.ke.wt[row] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const long cc = n0 + wn * 32 + j * 8 + 2 * t + e;
+                    if (!rlive || cc >= p.n) continue;
+                    const double q = fma(-2.0, acc[i][j][e], nzr + p.ke.nx[cc * p.ke.nx_stride]);
+                    double kap, ew;
+                    if (p.ke.kind == CGLB_MATERN32) kappa_and_dweight<CGLB_MATERN32>(q, s_tab, kap, ew);
+                    else kappa_and_dweight<CGLB_RBF>(q, s_tab, kap, ew);
+                    double* dst = p.C + row * p.ldc + cc;
+                    if (EPI == EPI_KMAP) {
+                        *dst = p.ke.variance * kap;
+                    } else {
+                        double G = (p.beta != 0.0) ? *dst : 0.0;            // beta != 0: a dense T is present
+                        if (p.ke.zvec) G = fma(wtr, p.ke.zvec[cc], G);
+                        const double gp = G * ew * p.ke.vc;
+                        *dst = gp;
+                        gk = fma(G, kap, gk);
+                        racc[i] += gp;
+                        cacc[j][e] += gp;
+                    }
+                }
+            }
+        }
+        if (EPI == EPI_KBWD) {
+            // rows: reduce over the 4 lanes sharing g; columns: over the 8 lanes sharing t
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double s = racc[i];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                const long row = m0 + wm * 64 + i * 8 + g;
+                if (t == 0 && row < p.m) atomicAdd(p.ke.rsum + row, s);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double s = cacc[j][e];
+                    s += __shfl_xor_sync(0xffffffffu, s, 4);
+                    s += __shfl_xor_sync(0xffffffffu, s, 8);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    const long cc = n0 + wn * 32 + j * 8 + 2 * t + e;
+                    if (g == 0 && cc < p.n) atomicAdd(p.ke.csum + cc, s);
+                }
+            gk = warp_sum(gk);
+            if (lane == 0) atomicAdd(p.ke.gk_sum, gk);
+        }
+        return;
+    }
+    if (!active) return;
+    // epilogue: lane holds (row g, cols 2t, 2t+1) of every 8x8 tile.  Per row group the (optional) reads of C
+    // are issued together before the dependent stores, as 16-byte accesses when C allows it.
+    const bool c_vec = ((p.ldc & 1) == 0) && (((uintptr_t)p.C & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long row = m0 + wm * 64 + i * 8 + g;
+        if (row >= p.m) continue;
+        if (EPI == EPI_STORE) {
+            double* crow = p.C + row * p.ldc;
+            double2 old[4];
+            bool full[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long col = n0 + wn * 32 + j * 8 + 2 * t;
+                full[j] = c_vec && (col + 1 < p.n);
+                old[j] = make_double2(0.0, 0.0);
+                if (p.beta != 0.0) {
+                    if (full[j]) old[j] = *reinterpret_cast<const double2*>(crow + col);
+                    else {
+                        if (col < p.n) old[j].x = crow[col];
+                        if (col + 1 < p.n) old[j].y = crow[col + 1];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long col = n0 + wn * 32 + j * 8 + 2 * t;
+                double2 v;
+                v.x = fma(p.beta, old[j].x, p.alpha * acc[i][j][0]);
+                v.y = fma(p.beta, old[j].y, p.alpha * acc[i][j][1]);
+                if (full[j]) *reinterpret_cast<double2*>(crow + col) = v;
+                else {
+                    if (col < p.n) crow[col] = v.x;
+                    if (col + 1 < p.n) crow[col + 1] = v.y;
+                }
+            }
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long col = n0 + wn * 32 + j * 8 + 2 * t;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long cc = col + e;
+                if (cc >= p.n) continue;
+                p.part[(long)blockIdx.z * p.part_stride + row * p.n + cc] = p.alpha * acc[i][j][e];
+            }
+        }
+    }
+}
+
 // C tile (bm, bn) of size 128x128; 8 warps as 2 (m) x 4 (n), warp tile 64x32 = 8x4 DMMA tiles.
 template <bool TRANSB, int EPI>
-__global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__(GTHREADS, 1) gemm_cpasync_kernel(const GemmArgs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
     double* sB = sA + GSTAGES * GemmSmem<TRANSB>::kA;
@@ -175,136 +305,154 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
     }
     cp_async_wait<0>();
 
-    if (EPI == EPI_KMAP || EPI == EPI_KBWD) {
-        __shared__ double s_tab[64];
-        __syncthreads();
-        if (tid < 64) s_tab[tid] = p.ke.exp_tab[tid];
-        __syncthreads();
-        double gk = 0.0, racc[8], cacc[4][2];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) racc[i] = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cacc[j][0] = cacc[j][1] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const long row = m0 + wm * 64 + i * 8 + g;
-            const bool rlive = row < p.m;
-            const double nzr = rlive ? p.ke.nz[row * p.ke.nz_stride] : 0.0;
-            const double wtr = (EPI == EPI_KBWD && rlive && p.ke.wt) ? p.ke.wt[row] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const long cc = n0 + wn * 32 + j * 8 + 2 * t + e;
-                    if (!rlive || cc >= p.n) continue;
-                    const double q = fma(-2.0, acc[i][j][e], nzr + p.ke.nx[cc * p.ke.nx_stride]);
-                    double kap, ew;
-                    if (p.ke.kind == CGLB_MATERN32) kappa_and_dweight<CGLB_MATERN32>(q, s_tab, kap, ew);
-                    else kappa_and_dweight<CGLB_RBF>(q, s_tab, kap, ew);
-                    double* dst = p.C + row * p.ldc + cc;
-                    if (EPI == EPI_KMAP) {
-                        *dst = p.ke.variance * kap;
-                    } else {
-                        double G = (p.beta != 0.0) ? *dst : 0.0;            // beta != 0: a dense T is present
-                        if (p.ke.zvec) G = fma(wtr, p.ke.zvec[cc], G);
-                        const double gp = G * ew * p.ke.vc;
-                        *dst = gp;
-                        gk = fma(G, kap, gk);
-                        racc[i] += gp;
-                        cacc[j][e] += gp;
-                    }
-                }
-            }
-        }
-        if (EPI == EPI_KBWD) {
-            // rows: reduce over the 4 lanes sharing g; columns: over the 8 lanes sharing t
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double s = racc[i];
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                const long row = m0 + wm * 64 + i * 8 + g;
-                if (t == 0 && row < p.m) atomicAdd(p.ke.rsum + row, s);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    double s = cacc[j][e];
-                    s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    s += __shfl_xor_sync(0xffffffffu, s, 8);
-                    s += __shfl_xor_sync(0xffffffffu, s, 16);
-                    const long cc = n0 + wn * 32 + j * 8 + 2 * t + e;
-                    if (g == 0 && cc < p.n) atomicAdd(p.ke.csum + cc, s);
-                }
-            gk = warp_sum(gk);
-            if (lane == 0) atomicAdd(p.ke.gk_sum, gk);
-        }
-        return;
+    gemm_epilogue<EPI>(p, acc, bm, bn, tid, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same GEMM with TMA operand staging (round 2): the operand tiles arrive through 1-D bulk copies (cp.async.bulk ->
+// UBLKCP, one per tile row, straight into the padded bank-conflict-free layouts above) on a GT_STAGES-deep full/empty
+// mbarrier ring.  Every warp stages 1/8 of the rows of a k-tile (one row per lane: lanes 0-15 a row of A, lanes 16-31 a row
+// of B) GT_STAGES - 1 tiles ahead, so the main loop has no CTA barrier, no cp.async address arithmetic (4 + 4 16-byte
+// copies per thread and k-tile before) and no wait_group; warps only meet through the barriers of a stage S - 1 tiles back.
+// (A ninth, dedicated producer warp would cap the kernel at 168 registers: three warps on one scheduler.)
+// Rows past the matrix and the K tail are written by the lane itself (zeros / the few valid doubles).  Needs 16-byte
+// aligned operand rows (lda, ldb even, aligned bases); anything else takes gemm_cpasync_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int GT_STAGES = 4;
+
+template <bool TRANSB>
+struct GemmTmaSmem {
+    static constexpr int kA = GM * GPITCH_K;
+    static constexpr int kB = TRANSB ? GN * GPITCH_K : GK * GPITCH_N;
+    static constexpr size_t bytes = (size_t)GT_STAGES * (kA + kB) * sizeof(double) + 2 * GT_STAGES * sizeof(uint64_t);
+};
+
+template <bool TRANSB, int EPI>
+__global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + GT_STAGES * GemmTmaSmem<TRANSB>::kA;
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(sB + GT_STAGES * GemmTmaSmem<TRANSB>::kB);
+    uint64_t* s_empty = s_full + GT_STAGES;
+
+    const int bm = blockIdx.y, bn = blockIdx.x;
+    if (p.lower_only && bn > bm) return;
+    const long m0 = (long)bm * GM, n0 = (long)bn * GN;
+    const long kbeg = (long)blockIdx.z * p.k_chunk;
+    long kend = kbeg + p.k_chunk;
+    if (kend > p.k) kend = p.k;
+    const int nkt = (int)((kend - kbeg + GK - 1) / GK);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    if (tid == 0) {
+        for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&s_full[s], GTHREADS); mbar_init(&s_empty[s], GTHREADS / 32); }
+        mbar_fence_init();
     }
-    // epilogue: lane holds (row g, cols 2t, 2t+1) of every 8x8 tile.  Per row group the (optional) reads of C
-    // are issued together before the dependent stores, as 16-byte accesses when C allows it.
-    const bool c_vec = ((p.ldc & 1) == 0) && (((uintptr_t)p.C & 15) == 0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const long row = m0 + wm * 64 + i * 8 + g;
-        if (row >= p.m) continue;
-        if (EPI == EPI_STORE) {
-            double* crow = p.C + row * p.ldc;
-            double2 old[4];
-            bool full[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const long col = n0 + wn * 32 + j * 8 + 2 * t;
-                full[j] = c_vec && (col + 1 < p.n);
-                old[j] = make_double2(0.0, 0.0);
-                if (p.beta != 0.0) {
-                    if (full[j]) old[j] = *reinterpret_cast<const double2*>(crow + col);
-                    else {
-                        if (col < p.n) old[j].x = crow[col];
-                        if (col + 1 < p.n) old[j].y = crow[col + 1];
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const long col = n0 + wn * 32 + j * 8 + 2 * t;
-                double2 v;
-                v.x = fma(p.beta, old[j].x, p.alpha * acc[i][j][0]);
-                v.y = fma(p.beta, old[j].y, p.alpha * acc[i][j][1]);
-                if (full[j]) *reinterpret_cast<double2*>(crow + col) = v;
-                else {
-                    if (col < p.n) crow[col] = v.x;
-                    if (col + 1 < p.n) crow[col + 1] = v.y;
-                }
-            }
-            continue;
+    __syncthreads();
+
+    // this lane's row of every k-tile: lanes 0-15 -> row 16 warp + lane of A; lanes 16-31 -> a row of B
+    long nval = p.n - n0;
+    if (nval > GN) nval = GN;
+    const bool is_a = lane < 16;
+    const int arow = warp * 16 + (lane & 15);                           // A (and NT B) tile row of this lane
+    const bool b_nn_lane = !TRANSB && !is_a && (lane & 15) < 2;         // NN: 16 rows of B per k-tile, 2 per warp
+    const int brow_nn = warp * 2 + (lane & 15);
+    int pstage = 0;
+    uint32_t pphase = 0;
+    auto stage_tile = [&](int kt) {
+        // wait until every warp has released the tile that lived in this stage, then fill this lane's row
+        mbar_wait(&s_empty[pstage], pphase ^ 1);
+        const long k0 = kbeg + (long)kt * GK;
+        const int kval = (int)((kend - k0) < GK ? (kend - k0) : GK);
+        double* dst = nullptr;
+        const double* src = nullptr;
+        int len = 0, valid = 0;
+        if (is_a) {
+            const long gr = m0 + arow;
+            dst = sA + pstage * GemmTmaSmem<TRANSB>::kA + arow * GPITCH_K;
+            src = p.A + (gr < p.m ? gr : 0) * p.lda + k0;
+            len = GK; valid = gr < p.m ? kval : 0;
+        } else if (TRANSB) {
+            const long gr = n0 + arow;
+            dst = sB + pstage * GemmTmaSmem<TRANSB>::kB + arow * GPITCH_K;
+            src = p.B + (gr < p.n ? gr : 0) * p.ldb + k0;
+            len = GK; valid = gr < p.n ? kval : 0;
+        } else if (b_nn_lane) {
+            const long gk = k0 + brow_nn;
+            dst = sB + pstage * GemmTmaSmem<TRANSB>::kB + brow_nn * GPITCH_N;
+            src = p.B + (gk < kend ? gk : kbeg) * p.ldb + n0;
+            len = GN; valid = gk < kend ? (int)nval : 0;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long col = n0 + wn * 32 + j * 8 + 2 * t;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const long cc = col + e;
-                if (cc >= p.n) continue;
-                p.part[(long)blockIdx.z * p.part_stride + row * p.n + cc] = p.alpha * acc[i][j][e];
-            }
+        if (len > 0 && valid == len) {
+            // full row: arrive with its byte count, then hand the copy to the TMA unit
+            mbar_expect_tx(&s_full[pstage], (uint32_t)(len * sizeof(double)));
+            tma_load_1d(dst, src, (uint32_t)(len * sizeof(double)), &s_full[pstage]);
+        } else {
+            for (int i = 0; i < len; ++i) dst[i] = (i < valid) ? src[i] : 0.0;      // partial / out-of-range row (or no row)
+            mbar_arrive(&s_full[pstage]);
         }
+        if (++pstage == GT_STAGES) { pstage = 0; pphase ^= 1; }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll 1
+    for (int kt = 0; kt < GT_STAGES - 1 && kt < nkt; ++kt) stage_tile(kt);
+    int stage = 0;
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int kt = 0; kt < nkt; ++kt) {
+        if (kt + GT_STAGES - 1 < nkt) stage_tile(kt + GT_STAGES - 1);
+        mbar_wait(&s_full[stage], phase);
+        const double* a = sA + stage * GemmTmaSmem<TRANSB>::kA + (wm * 64 + g) * GPITCH_K + t;
+        const double* b = TRANSB ? sB + stage * GemmTmaSmem<TRANSB>::kB + (wn * 32 + g) * GPITCH_K + t
+                                 : sB + stage * GemmTmaSmem<TRANSB>::kB + t * GPITCH_N + wn * 32 + g;
+#pragma unroll
+        for (int k4 = 0; k4 < GK / 4; ++k4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = a[i * 8 * GPITCH_K + k4 * 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = TRANSB ? b[j * 8 * GPITCH_K + k4 * 4] : b[k4 * 4 * GPITCH_N + j * 8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);
+        if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
     }
+    gemm_epilogue<EPI>(p, acc, bm, bn, tid, true);
 }
 
 template <bool TRANSB, int EPI>
 static int launch_gemm(Context* ctx, const GemmArgs& p, int ksplit, cudaStream_t st) {
     if (p.m <= 0 || p.n <= 0) return CGLB_OK;
-    auto kern = gemm_kernel<TRANSB, EPI>;
-    size_t smem = GemmSmem<TRANSB>::bytes;
-    CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((p.n + GN - 1) / GN), (unsigned)((p.m + GM - 1) / GM), (unsigned)ksplit);
     if (grid.y > 65535 || grid.z > 65535) {
         set_error("gemm: m=%ld too large for grid.y", p.m);
         return CGLB_ERR_UNSUPPORTED;
     }
-    kern<<<grid, GTHREADS, smem, st>>>(p);
+    // bulk copies need 16-byte aligned rows (and k-tiles that start on an even column: k_chunk is a multiple of GK)
+    const bool tma_ok = ((p.lda & 1) == 0) && ((p.ldb & 1) == 0) && (((uintptr_t)p.A & 15) == 0) && (((uintptr_t)p.B & 15) == 0);
+    if (tma_ok) {
+        auto kern = gemm_kernel<TRANSB, EPI>;
+        size_t smem = GemmTmaSmem<TRANSB>::bytes;
+        CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, GTHREADS, smem, st>>>(p);
+    } else {
+        auto kern = gemm_cpasync_kernel<TRANSB, EPI>;
+        size_t smem = GemmSmem<TRANSB>::bytes;
+        CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, GTHREADS, smem, st>>>(p);
+    }
     ctx->launches++;
     CGLB_LAUNCH_OK();
     return CGLB_OK;
