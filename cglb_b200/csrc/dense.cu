@@ -312,13 +312,15 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_cpasync_kernel(const GemmArg
 // The same GEMM with TMA operand staging (round 2): the operand tiles arrive through 1-D bulk copies (cp.async.bulk ->
 // UBLKCP, one per tile row, straight into the padded bank-conflict-free layouts above) on a GT_STAGES-deep full/empty
 // mbarrier ring.  Every warp stages 1/8 of the rows of a k-tile (one row per lane: lanes 0-15 a row of A, lanes 16-31 a row
-// of B) GT_STAGES - 1 tiles ahead, so the main loop has no CTA barrier, no cp.async address arithmetic (4 + 4 16-byte
+// of B; one mbarrier arrival per warp) GT_STAGES - 1 tiles ahead, so the main loop has no CTA barrier, no cp.async address arithmetic (4 + 4 16-byte
 // copies per thread and k-tile before) and no wait_group; warps only meet through the barriers of a stage S - 1 tiles back.
 // (A ninth, dedicated producer warp would cap the kernel at 168 registers: three warps on one scheduler.)
 // Rows past the matrix and the K tail are written by the lane itself (zeros / the few valid doubles).  Needs 16-byte
 // aligned operand rows (lda, ldb even, aligned bases); anything else takes gemm_cpasync_kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int GT_STAGES = 4;
+constexpr int GT_STAGES = 5;
+constexpr int GT_AHEAD = GT_STAGES - 2;      // tiles in flight ahead of the one being multiplied: a stage is refilled two tiles after
+                                            // its last use, so a warp never waits for the warps that are one tile behind it
 
 template <bool TRANSB>
 struct GemmTmaSmem {
@@ -335,7 +337,10 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
     uint64_t* s_full = reinterpret_cast<uint64_t*>(sB + GT_STAGES * GemmTmaSmem<TRANSB>::kB);
     uint64_t* s_empty = s_full + GT_STAGES;
 
-    const int bm = blockIdx.y, bn = blockIdx.x;
+    // tile order: the row tile runs fastest, so the CTAs in flight together share one column panel of B (L2-resident) and
+    // all of A's row tiles; with bn fastest the (M x M)(M x n) product read B 16 times from DRAM (26.6 GB for 1.6 GB, ncu)
+    const long lin = (long)blockIdx.y * gridDim.x + blockIdx.x;
+    const int bm = (int)(lin % gridDim.y), bn = (int)(lin / gridDim.y);
     if (p.lower_only && bn > bm) return;
     const long m0 = (long)bm * GM, n0 = (long)bn * GN;
     const long kbeg = (long)blockIdx.z * p.k_chunk;
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp >> 2, wn = warp & 3;
     if (tid == 0) {
-        for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&s_full[s], GTHREADS); mbar_init(&s_empty[s], GTHREADS / 32); }
+        for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&s_full[s], GTHREADS / 32); mbar_init(&s_empty[s], GTHREADS / 32); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -385,14 +390,20 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
             src = p.B + (gk < kend ? gk : kbeg) * p.ldb + n0;
             len = GN; valid = gk < kend ? (int)nval : 0;
         }
-        if (len > 0 && valid == len) {
-            // full row: arrive with its byte count, then hand the copy to the TMA unit
-            mbar_expect_tx(&s_full[pstage], (uint32_t)(len * sizeof(double)));
-            tma_load_1d(dst, src, (uint32_t)(len * sizeof(double)), &s_full[pstage]);
-        } else {
-            for (int i = 0; i < len; ++i) dst[i] = (i < valid) ? src[i] : 0.0;      // partial / out-of-range row (or no row)
-            mbar_arrive(&s_full[pstage]);
+        // partial / out-of-range rows are written by the lane itself; full rows go to the TMA unit.  One arrival per warp:
+        // lane 0 arrives with the bytes of the warp's full rows after the warp's plain stores (release), then the copies go out.
+        const bool full = len > 0 && valid == len;
+        if (!full)
+            for (int i = 0; i < len; ++i) dst[i] = (i < valid) ? src[i] : 0.0;
+        const unsigned fmask = __ballot_sync(0xffffffffu, full);
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(__popc(fmask & 0xffffu) * GK * sizeof(double)) +
+                                   (uint32_t)(__popc(fmask >> 16) * (TRANSB ? GK : GN) * sizeof(double));
+            if (bytes) mbar_expect_tx(&s_full[pstage], bytes);
+            else mbar_arrive(&s_full[pstage]);
         }
+        __syncwarp();
+        if (full) tma_load_1d(dst, src, (uint32_t)(len * sizeof(double)), &s_full[pstage]);
         if (++pstage == GT_STAGES) { pstage = 0; pphase ^= 1; }
     };
 
@@ -403,12 +414,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(const GemmArgs p) {
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll 1
-    for (int kt = 0; kt < GT_STAGES - 1 && kt < nkt; ++kt) stage_tile(kt);
+    for (int kt = 0; kt < GT_AHEAD && kt < nkt; ++kt) stage_tile(kt);
     int stage = 0;
     uint32_t phase = 0;
+    // (loading the fragments one k4-step ahead across the k-tile boundary through a second register set was measured and is
+    // slower: 28.6 vs 31.7 TFLOP/s at 2048 x 200k x 2048 -- 214-222 registers instead of 178-198)
 #pragma unroll 1
     for (int kt = 0; kt < nkt; ++kt) {
-        if (kt + GT_STAGES - 1 < nkt) stage_tile(kt + GT_STAGES - 1);
+        if (kt + GT_AHEAD < nkt) stage_tile(kt + GT_AHEAD);
         mbar_wait(&s_full[stage], phase);
         const double* a = sA + stage * GemmTmaSmem<TRANSB>::kA + (wm * 64 + g) * GPITCH_K + t;
         const double* b = TRANSB ? sB + stage * GemmTmaSmem<TRANSB>::kB + (wn * 32 + g) * GPITCH_K + t
