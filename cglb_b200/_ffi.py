@@ -21,6 +21,7 @@ SIGNATURES = {
     "cglb_last_error": (C.c_char_p, []),
     "cglb_create": (c_int, [C.POINTER(C.c_void_p), c_int]),
     "cglb_destroy": (c_int, [C.c_void_p]),
+    "cglb_set_option": (c_int, [C.c_void_p, C.c_char_p, c_long]),
     "cglb_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "cglb_num_sms": (c_int, [C.c_void_p]),
     "cglb_packed_width": (c_int, [c_int]),

@@ -61,6 +61,9 @@ struct Context {
     double* exp_table;    // [64] 2^(j/64) followed by [1024] 2^(j/1024) with j << 10 subtracted from the high word
                           // (fast_exp_neg<10>); staged into shared memory by the kernels
     unsigned long long launches;   // number of kernels this context launched (bench.py gpu_launches)
+    // developer options (cglb_set_option; initialised from the environment once, at cglb_create)
+    int opt_dsweep;        // 0: register-resident sweeps only, 1: size/dimension policy (default), 2: DMMA sweeps wherever possible
+    int opt_gemm_staging;  // 1: cp.async ring (default), 2: TMA bulk-copy ring for aligned operands
 };
 
 // the first kScratchScalars doubles of Context::scratch hold the scalar accumulators of the sweeps

@@ -1,5 +1,6 @@
 // Context lifetime, error text, workspaces.
 #include <math.h>
+#include <stdlib.h>
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -90,6 +91,12 @@ extern "C" int cglb_create(cglb_context** out, int device) {
     memset(ctx, 0, sizeof(Context));
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    {
+        const char* e = getenv("CGLB_DSWEEP");
+        ctx->opt_dsweep = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+        e = getenv("CGLB_GEMM_STAGING");
+        ctx->opt_gemm_staging = (e && e[0] == '2') ? 2 : 1;
+    }
     CGLB_CUDA_OK(cudaMalloc(&ctx->counters, sizeof(int) * 16));
     CGLB_CUDA_OK(cudaMemset(ctx->counters, 0, sizeof(int) * 16));
     static double tab[kExpTabSmall + kExpTabBig];
@@ -106,6 +113,23 @@ extern "C" int cglb_create(cglb_context** out, int device) {
     CGLB_CUDA_OK(cudaMemcpy(ctx->exp_table, tab, sizeof(tab), cudaMemcpyHostToDevice));
     *out = reinterpret_cast<cglb_context*>(ctx);
     return CGLB_OK;
+}
+
+extern "C" int cglb_set_option(cglb_context* c, const char* name, long value) {
+    Context* ctx = reinterpret_cast<Context*>(c);
+    CGLB_CHECK_ARG(ctx && name, "null pointer");
+    if (strcmp(name, "dsweep") == 0) {
+        CGLB_CHECK_ARG(value >= 0 && value <= 2, "dsweep: 0, 1 or 2");
+        ctx->opt_dsweep = (int)value;
+        return CGLB_OK;
+    }
+    if (strcmp(name, "gemm_staging") == 0) {
+        CGLB_CHECK_ARG(value == 1 || value == 2, "gemm_staging: 1 (cp.async) or 2 (TMA)");
+        ctx->opt_gemm_staging = (int)value;
+        return CGLB_OK;
+    }
+    set_error("cglb_set_option: unknown option '%s'", name);
+    return CGLB_ERR_ARG;
 }
 
 extern "C" int cglb_destroy(cglb_context* c) {

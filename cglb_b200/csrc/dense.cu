@@ -10,6 +10,7 @@
 // (cuSOLVER dpotrf, cuBLAS dtrsm/dgemm).  FP64 has no tcgen05 form; mma.sync.m8n8k4.f64 (DMMA) measured
 // 37.1 TFLOP/s on this B200 vs 34.2 for plain DFMA (profiles/fp64_peaks_r01.json), so the contraction
 // runs on DMMA.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "kmv_impl.cuh"
@@ -454,7 +455,11 @@ static int launch_gemm(Context* ctx, const GemmArgs& p, int ksplit, cudaStream_t
         return CGLB_ERR_UNSUPPORTED;
     }
     // bulk copies need 16-byte aligned rows (and k-tiles that start on an even column: k_chunk is a multiple of GK)
-    const bool tma_ok = ((p.lda & 1) == 0) && ((p.ldb & 1) == 0) && (((uintptr_t)p.A & 15) == 0) && (((uintptr_t)p.B & 15) == 0);
+    // Default: the cp.async ring.  The TMA-staged kernel is selected with cglb_set_option("gemm_staging", 2): it matches the
+    // cp.async kernel on the one big (M x M)(M x n) product (32.0 vs 31.8 TFLOP/s) and loses everywhere else (TRSM block rows
+    // 13.4 vs 26.4 TFLOP/s at 2048 x 54k, the kin40k-shaped step 23.4 vs 21.6 ms).
+    const bool tma_ok = ctx->opt_gemm_staging == 2 && ((p.lda & 1) == 0) && ((p.ldb & 1) == 0) && (((uintptr_t)p.A & 15) == 0) &&
+                        (((uintptr_t)p.B & 15) == 0);
     if (tma_ok) {
         auto kern = gemm_kernel<TRANSB, EPI>;
         size_t smem = GemmTmaSmem<TRANSB>::bytes;

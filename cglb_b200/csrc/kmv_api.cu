@@ -240,20 +240,17 @@ int wide_bwd_sweep(Context* ctx, int kind, const double* xp, long n, int d, cons
 bool dsweep_supported(const Context* ctx, int d, long n, int nparts);
 bool dbwd_supported(const Context* ctx, int d, long n, int nparts);
 
-// developer switch: CGLB_DSWEEP=0 routes every d <= 32 symmetric sweep through the register-resident kernel,
-// CGLB_DSWEEP=2 forces the DMMA sweep wherever the packed width allows it (tests of small shapes)
-static int dsweep_mode() {
-    const char* e = getenv("CGLB_DSWEEP");
-    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
-}
+// developer option "dsweep" (cglb_set_option; read from CGLB_DSWEEP once at cglb_create): 0 routes every d <= 32 symmetric sweep
+// through the register-resident kernel, 2 forces the DMMA sweep wherever the packed width allows it (tests of small shapes)
+static int dsweep_mode(const Context* ctx) { return ctx->opt_dsweep; }
 
 static int dispatch(Context* ctx, int kind, int d, int mode, const SweepArgs& a, cudaStream_t st) {
     if (mode == 0 && d <= CGLB_MAX_REGISTER_D) {
-        const int dm = dsweep_mode();
+        const int dm = dsweep_mode(ctx);
         if (dm != 0 && dsweep_supported(ctx, d, a.nrows, dm == 2 ? 0 : a.nparts)) mode = 3;
     }
     if (mode == 2 && d <= CGLB_MAX_REGISTER_D) {
-        const int dm = dsweep_mode();
+        const int dm = dsweep_mode(ctx);
         if (dm != 0 && dbwd_supported(ctx, d, a.nrows, dm == 2 ? 0 : a.nparts)) mode = 4;
     }
     if (d > CGLB_MAX_REGISTER_D && mode == 2)
@@ -394,7 +391,7 @@ extern "C" int cglb_kmv_sym_variant(const cglb_context* c, int d, long n, int np
     const Context* ctx = reinterpret_cast<const Context*>(c);
     if (!ctx || d < 1 || n < 0 || nparts < 1) return CGLB_ERR_ARG;
     if (d > CGLB_MAX_REGISTER_D) return 2;
-    const int dm = dsweep_mode();
+    const int dm = dsweep_mode(ctx);
     return (dm != 0 && dsweep_supported(ctx, d, n, dm == 2 ? 0 : nparts)) ? 1 : 0;
 }
 

@@ -65,6 +65,7 @@ class Engine:
         handle = C.c_void_p()
         check(self.lib.cglb_create(C.byref(handle), device_index), "cglb_create")
         self.ctx = handle
+        self._env_seen = {}
         # optional per-kernel CUDA-event timing (bench.py roofline): name -> list of (start, end) events
         self.timing = None
 
@@ -87,6 +88,26 @@ class Engine:
         """name -> (launches, total ms).  Synchronises."""
         torch.cuda.synchronize(self.device)
         return {k: (len(v), float(sum(a.elapsed_time(b) for a, b in v))) for k, v in (self.timing or {}).items()}
+
+    # ---- developer options ----------------------------------------------------------------------
+    def set_option(self, name: str, value: int):
+        """cglb_set_option: "dsweep" 0 / 1 / 2, "gemm_staging" 1 (cp.async) / 2 (TMA)."""
+        check(self.lib.cglb_set_option(self.ctx, name.encode(), int(value)), "cglb_set_option")
+
+    _ENV_OPTIONS = {"CGLB_DSWEEP": ("dsweep", 1), "CGLB_GEMM_STAGING": ("gemm_staging", 1)}
+
+    def _sync_env_options(self):
+        """The library reads its switches from the environment once (cglb_create); tests and tools flip them at run time, so
+        the Python wrapper forwards a changed value before the calls they affect (no getenv on the C side's dispatch path)."""
+        import os
+        for var, (name, default) in self._ENV_OPTIONS.items():
+            val = os.environ.get(var)
+            if self._env_seen.get(var, "__unset__") != val:
+                self._env_seen[var] = val
+                try:
+                    self.set_option(name, int(val) if val not in (None, "") else default)
+                except (ValueError, CglbError):
+                    self.set_option(name, default)
 
     # ---- bookkeeping ---------------------------------------------------------------------------
     def stream(self):
@@ -130,10 +151,12 @@ class Engine:
 
     def kmv_sym_variant(self, d: int, n: int, nparts: int = 1) -> int:
         """which kernel cglb_kmv_sym launches for this shape (include/cglb_b200.h)"""
+        self._sync_env_options()
         return int(self.lib.cglb_kmv_sym_variant(self.ctx, int(d), int(n), int(nparts)))
 
     def kmv_sym(self, kind, xp, n, d, v, variance, diag, out=None, part=0, nparts=1) -> Tensor:
         _req(xp, "xp"); _req(v, "v")
+        self._sync_env_options()
         if out is None:
             out = self.empty(n)
         self._timed("kmv_sym", lambda: check(self.lib.cglb_kmv_sym(
@@ -191,6 +214,7 @@ class Engine:
 
     def kmv_bwd_sym(self, kind, xp, n, d, u, w, variance, lengthscale, out, part=0, nparts=1) -> Tensor:
         _req(xp, "xp"); _req(u, "u"); _req(w, "w"); _req(lengthscale, "lengthscale"); _req(out, "out")
+        self._sync_env_options()
         self._timed("kmv_bwd_sym", lambda: check(self.lib.cglb_kmv_bwd_sym(
             self.ctx, KIND_IDS[kind], ptr(xp), n, d, ptr(u), ptr(w), float(variance), ptr(lengthscale), ptr(out), int(part),
             int(nparts), self.stream()), "cglb_kmv_bwd_sym"))
@@ -244,6 +268,7 @@ class Engine:
     def gemm(self, a: Tensor, b: Tensor, out: Tensor, m: int, n: int, k: int, transb: bool = False, alpha: float = 1.0,
              beta: float = 0.0) -> Tensor:
         _req(a, "a"); _req(b, "b"); _req(out, "out")
+        self._sync_env_options()
         self._timed("gemm", lambda: check(self.lib.cglb_gemm(
             self.ctx, int(transb), m, n, k, float(alpha), ptr(a), a.stride(0), ptr(b), b.stride(0), float(beta), ptr(out),
             out.stride(0), self.stream()), "cglb_gemm"))

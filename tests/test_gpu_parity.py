@@ -613,30 +613,44 @@ def test_dense_factorisations(eng, m):
 @pytest.mark.parametrize("m,n,k,transb", [(128, 128, 16, False), (130, 257, 100, False), (300, 200, 333, True), (64, 1000, 2048, True),
                                           (2048, 160, 4000, False), (1, 1, 5, True), (257, 129, 1, False)])
 def test_gemm_both_staging_paths(eng, m, n, k, transb):
-    """cglb_gemm: the TMA-staged kernel (16-byte aligned operand rows: even leading dimensions) and the cp.async kernel it falls
-    back to (odd leading dimension), ragged edge tiles, K tails, the split-K route for few tiles and a long K, beta != 0."""
+    """cglb_gemm with both operand-staging kernels -- the cp.async ring (default) and the TMA bulk-copy ring
+    (cglb_set_option "gemm_staging" 2; 16-byte aligned operand rows only, odd leading dimensions fall back) -- on ragged edge
+    tiles, K tails, the split-K route for few tiles and a long K, beta != 0."""
     g = torch.Generator().manual_seed(m * 7 + n)
     dev = eng.device
-    for pad in (0, 1):                     # pad = 1: odd leading dimensions -> rows are not 16-byte aligned -> cp.async path
-        lda = k + (k & 1) + pad
-        a_buf = torch.randn(m, lda, generator=g, dtype=f64).to(dev)
-        a = a_buf[:, :k]
-        if transb:
-            ldb = k + (k & 1) + pad
-            b_buf = torch.randn(n, ldb, generator=g, dtype=f64).to(dev)
-            b = b_buf[:, :k]
-            ref = a @ b.t()
-        else:
-            ldb = n + (n & 1) + pad
-            b_buf = torch.randn(k, ldb, generator=g, dtype=f64).to(dev)
-            b = b_buf[:, :n]
-            ref = a @ b
-        ldc = n + (n & 1)
-        c_buf = torch.randn(m, ldc, generator=g, dtype=f64).to(dev)
-        c0 = c_buf[:, :n].clone()
-        check_rc = eng.lib.cglb_gemm(eng.ctx, int(transb), m, n, k, 0.7, a_buf.data_ptr(), lda, b_buf.data_ptr(), ldb, -0.3,
-                                     c_buf.data_ptr(), ldc, eng.stream())
-        assert check_rc == 0
-        want = 0.7 * ref - 0.3 * c0
-        err = float((c_buf[:, :n] - want).abs().max() / (want.abs().max() + 1e-300))
-        assert err <= 1e-12, (pad, err)
+    try:
+        for staging in (1, 2):
+            eng.set_option("gemm_staging", staging)
+            for pad in (0, 1):                 # pad = 1: odd leading dimensions -> rows are not 16-byte aligned
+                lda = k + (k & 1) + pad
+                a_buf = torch.randn(m, lda, generator=g, dtype=f64).to(dev)
+                a = a_buf[:, :k]
+                if transb:
+                    ldb = k + (k & 1) + pad
+                    b_buf = torch.randn(n, ldb, generator=g, dtype=f64).to(dev)
+                    ref = a @ b_buf[:, :k].t()
+                else:
+                    ldb = n + (n & 1) + pad
+                    b_buf = torch.randn(k, ldb, generator=g, dtype=f64).to(dev)
+                    ref = a @ b_buf[:, :n]
+                ldc = n + (n & 1)
+                c_buf = torch.randn(m, ldc, generator=g, dtype=f64).to(dev)
+                c0 = c_buf[:, :n].clone()
+                rc = eng.lib.cglb_gemm(eng.ctx, int(transb), m, n, k, 0.7, a_buf.data_ptr(), lda, b_buf.data_ptr(), ldb, -0.3,
+                                       c_buf.data_ptr(), ldc, eng.stream())
+                assert rc == 0
+                want = 0.7 * ref - 0.3 * c0
+                err = float((c_buf[:, :n] - want).abs().max() / (want.abs().max() + 1e-300))
+                assert err <= 1e-12, (staging, pad, err)
+    finally:
+        eng.set_option("gemm_staging", 1)
+
+
+def test_dense_factorisations_with_tma_staging(eng):
+    """potrf / tri_inverse / trsm / syrk through the TMA-staged GEMM (in-place panel and block-row products included)."""
+    try:
+        eng.set_option("gemm_staging", 2)
+        test_dense_factorisations(eng, 200)
+        test_dense_factorisations(eng, 1024)
+    finally:
+        eng.set_option("gemm_staging", 1)
