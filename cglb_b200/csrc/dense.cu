@@ -34,7 +34,7 @@ struct KEpiArgs {
     const double* nx; long nx_stride;
     const double* exp_tab;
     const double* wt; const double* zvec;  // may be null
-    double* rsum; double* csum; double* gk_sum;
+    double* rsum; double* csum; double* gk_sum;   // EPI_KBWD partial slots: [column tiles][m], [row tiles][n], [row tiles][column tiles]
     double variance, vc;
     int kind;
 };
@@ -94,10 +94,10 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& p, double (&acc)[8
     const long m0 = (long)bm * GM, n0 = (long)bn * GN;
     if (EPI == EPI_KMAP || EPI == EPI_KBWD) {
         __shared__ double s_tab[64];
+        __shared__ double s_rs[4][GM], s_cs[2][GN], s_gk[8];      // EPI_KBWD: per-warp row / column / G*kappa sums
         __syncthreads();
         if (tid < 64) s_tab[tid] = p.ke.exp_tab[tid];
         __syncthreads();
-        if (!active) return;
         double gk = 0.0, racc[8], cacc[4][2];
 #pragma unroll
         for (int i = 0; i < 8; ++i) racc[i] = 0.0;
@@ -141,8 +141,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& p, double (&acc)[8
                 double s = racc[i];
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
-                const long row = m0 + wm * 64 + i * 8 + g;
-                if (t == 0 && row < p.m) atomicAdd(p.ke.rsum + row, s);
+                if (t == 0) s_rs[wn][wm * 64 + i * 8 + g] = s;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -152,11 +151,28 @@ __device__ __forceinline__ void gemm_epilogue(const GemmArgs& p, double (&acc)[8
                     s += __shfl_xor_sync(0xffffffffu, s, 4);
                     s += __shfl_xor_sync(0xffffffffu, s, 8);
                     s += __shfl_xor_sync(0xffffffffu, s, 16);
-                    const long cc = n0 + wn * 32 + j * 8 + 2 * t + e;
-                    if (g == 0 && cc < p.n) atomicAdd(p.ke.csum + cc, s);
+                    if (g == 0) s_cs[wm][wn * 32 + j * 8 + 2 * t + e] = s;
                 }
             gk = warp_sum(gk);
-            if (lane == 0) atomicAdd(p.ke.gk_sum, gk);
+            if (lane == 0) s_gk[warp] = gk;
+        }
+        if (EPI == EPI_KBWD) {
+            // fixed summation order: the warps' sums are combined in warp order, every CTA stores its row / column / G*kappa
+            // sums in its own slot (rsum: [column tile][m], csum: [row tile][n], gk: [row tile][column tile]);
+            // kbwd_reduce_kernel adds the slots in tile order
+            __syncthreads();
+            if (tid < GM) {
+                const long row = m0 + tid;
+                if (row < p.m) p.ke.rsum[(long)bn * p.m + row] = s_rs[0][tid] + s_rs[1][tid] + s_rs[2][tid] + s_rs[3][tid];
+            } else if (tid < GM + GN) {
+                const long cc = n0 + (tid - GM);
+                if (cc < p.n) p.ke.csum[(long)bm * p.n + cc] = s_cs[0][tid - GM] + s_cs[1][tid - GM];
+            }
+            if (tid == 0) {
+                double s = 0.0;
+                for (int w8 = 0; w8 < 8; ++w8) s += s_gk[w8];
+                p.ke.gk_sum[(long)bm * gridDim.x + bn] = s;
+            }
         }
         return;
     }
@@ -823,6 +839,28 @@ __global__ void knm_wide_assemble_kernel(const double* __restrict__ zp, long m, 
     }
 }
 
+// second stage of the EPI_KBWD sums: slots added in tile order (fixed summation order)
+__global__ void kbwd_reduce_kernel(const double* __restrict__ rpart, const double* __restrict__ cpart, const double* __restrict__ gpart,
+                                   long m, long n, long tiles_m, long tiles_n, double* __restrict__ rsum, double* __restrict__ csum,
+                                   double* __restrict__ gk) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) {
+        double s = 0.0;
+        for (long b = 0; b < tiles_n; ++b) s += rpart[b * m + i];
+        rsum[i] = s;
+    } else if (i < m + n) {
+        const long c = i - m;
+        double s = 0.0;
+        for (long b = 0; b < tiles_m; ++b) s += cpart[b * n + c];
+        csum[c] = s;
+    }
+    if (i == 0) {
+        double s = 0.0;
+        for (long b = 0; b < tiles_m * tiles_n; ++b) s += gpart[b];
+        *gk = s;
+    }
+}
+
 int knm_build_wide(Context* ctx, int kind, const double* zp, long m, const double* xp, long n, int d, double variance,
                    double* out, long ld, cudaStream_t st) {
     const int kp = wide_kp(d), w = packed_width(d);
@@ -841,7 +879,7 @@ int knm_backward_wide(Context* ctx, int kind, const double* zp, long m, const do
         return CGLB_ERR_UNSUPPORTED;
     }
     const int kp = wide_kp(d), w = packed_width(d);
-    // workspace: [rsum m | csum ncols | gk 1 | gx m*kp]
+    // workspace: [rsum m | csum ncols | gk 1 | gx m*kp] in scratch; the epilogue's per-CTA partial slots in ypart
     const long need = m + ncols + 1 + m * kp;
     int rc = ensure_scratch(ctx, kScratchScalars + need);
     if (rc) return rc;
@@ -849,15 +887,23 @@ int knm_backward_wide(Context* ctx, int kind, const double* zp, long m, const do
     double* csum = rsum + m;
     double* gk = csum + ncols;
     double* gx = gk + 1;
-    CGLB_CUDA_OK(cudaMemsetAsync(rsum, 0, sizeof(double) * need, st));
+    const long tiles_m = (m + GM - 1) / GM, tiles_n = (ncols + GN - 1) / GN;
+    rc = ensure_ypart(ctx, tiles_n * m + tiles_m * ncols + tiles_m * tiles_n);
+    if (rc) return rc;
+    double* rpart = ctx->ypart;
+    double* cpart = rpart + tiles_n * m;
+    double* gpart = cpart + tiles_m * ncols;
     KEpiArgs ke{};
     ke.nz = zp + kp; ke.nz_stride = w; ke.nx = xp + kp; ke.nx_stride = w; ke.exp_tab = ctx->exp_table;
-    ke.wt = wt; ke.zvec = zvec; ke.rsum = rsum; ke.csum = csum; ke.gk_sum = gk;
+    ke.wt = wt; ke.zvec = zvec; ke.rsum = rpart; ke.csum = cpart; ke.gk_sum = gpart;
     ke.variance = variance; ke.vc = variance * ((kind == CGLB_MATERN32) ? 1.0 : 2.0); ke.kind = kind;
     // S = Zp Xp^T, epilogue writes GP over t (beta = 1 flags "t holds a dense G part")
     GemmArgs p{zp, w, xp, w, t, ldt, m, ncols, kp, (kp + GK - 1) / GK * GK, 1.0, 1.0, 0, ke};
     rc = launch_gemm<true, EPI_KBWD>(ctx, p, 1, st);
     if (rc) return rc;
+    kbwd_reduce_kernel<<<(unsigned)((m + ncols + 255) / 256), 256, 0, st>>>(rpart, cpart, gpart, m, ncols, tiles_m, tiles_n, rsum, csum, gk);
+    ctx->launches++;
+    CGLB_LAUNCH_OK();
     // GX = GP * Xp (coordinates): split-K over the columns
     long tiles = (m + GM - 1) / GM;
     long want = (2L * ctx->num_sms + tiles - 1) / tiles;

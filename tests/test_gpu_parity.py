@@ -425,18 +425,19 @@ def test_recomputed_residual_route_on_the_golden_trajectories(name):
 def test_repeated_evaluations_are_bitwise_identical(eng):
     """Fixed summation order (SURVEY.md section 7 risk 5): per-CTA copies + ordered second stage in the sweeps, ordered
     partials in the preconditioner GEMVs and the split-K GEMMs.  Two runs of the same CG trajectory give the same bits."""
-    g = np.load(os.path.join(GOLDEN_DIR, "kin_like_rbf.npz"))
-    outs = []
-    for rep in range(2):
-        model = make_model(str(g["kind"]), g["x"], g["y"], g["z"], float(g["noise"]), float(g["variance"]), g["lengthscale"], float(g["mean_c"]))
-        lb = cb.LowerBoundCG(model)
-        loss = -lb((model.train_inputs[0], model.train_targets))
-        grads = torch.autograd.grad(loss, list(model.parameters()))
-        outs.append((float(loss), int(model.cg_stats.steps), model.v_vec.detach().cpu().clone(), [g_.cpu().clone() for g_ in grads]))
-    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
-    assert torch.equal(outs[0][2], outs[1][2])
-    for ga, gb in zip(outs[0][3], outs[1][3]):          # d <= 32: the K_nm backward and the split-K GEMMs are ordered too
-        assert torch.equal(ga, gb)
+    for case in ("kin_like_rbf", "song_like_wide"):          # d = 8 (register / DMMA kernels) and d > 32 (wide kernels, GEMM epilogues)
+        g = np.load(os.path.join(GOLDEN_DIR, f"{case}.npz"))
+        outs = []
+        for rep in range(2):
+            model = make_model(str(g["kind"]), g["x"], g["y"], g["z"], float(g["noise"]), float(g["variance"]), g["lengthscale"], float(g["mean_c"]))
+            lb = cb.LowerBoundCG(model)
+            loss = -lb((model.train_inputs[0], model.train_targets))
+            grads = torch.autograd.grad(loss, list(model.parameters()))
+            outs.append((float(loss), int(model.cg_stats.steps), model.v_vec.detach().cpu().clone(), [g_.cpu().clone() for g_ in grads]))
+        assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1], case
+        assert torch.equal(outs[0][2], outs[1][2]), case
+        for ga, gb in zip(outs[0][3], outs[1][3]):          # the K_nm backward and the split-K GEMMs are ordered too
+            assert torch.equal(ga, gb), case
     # the sweeps themselves, on the three kernels (register-resident, DMMA distance, wide)
     for n, d, mode in ((3000, 3, "0"), (3000, 11, "2"), (1500, 40, "1")):
         os.environ["CGLB_DSWEEP"] = mode
