@@ -96,6 +96,10 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
+        return self.summary()
+
+    def summary(self):
+        """clocks / throttle reasons of the samples taken so far (also used for the cumulative lines of long runs)"""
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
         reasons = set()
@@ -126,6 +130,14 @@ def run_reference(args, rank):
     if args.n:
         n = args.n
     th = THETAS[args.theta]
+    # all the host threads this process may use: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would
+    # make the CPU arm 16-32x slower under the N > 1 launch line than under the N = 1 one
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if avail > torch.get_num_threads():
+        torch.set_num_threads(avail)
     threads = torch.get_num_threads()
     ls = torch.full((1, d), th["ls"](d), dtype=torch.float64)
     var = torch.tensor(th["variance"], dtype=torch.float64)
@@ -495,7 +507,8 @@ def run_b200(args, rank, world, local_rank):
         if rank == 0 and td > 5e3 and i + 1 < args.steps:
             # long steps (n = 2M on 1-2 GPUs): leave a parsable cumulative line behind after every step, in case the
             # process is killed at an outer limit; the complete line comes last
-            print(json.dumps(make_line(True, launches=per_step[-1][0], ksum=per_step[-1][1], kt=per_step[-1][2])), flush=True)
+            print(json.dumps(make_line(True, clocks=sampler.summary() if sampler else None, launches=per_step[-1][0],
+                                       ksum=per_step[-1][1], kt=per_step[-1][2])), flush=True)
     if truncated and len(stats) > 3 and len(stats) % 3:
         keep = len(stats) - len(stats) % 3
         del stats[keep:]
