@@ -64,6 +64,7 @@ struct Context {
     // developer options (cglb_set_option; initialised from the environment once, at cglb_create)
     int opt_dsweep;        // 0: register-resident sweeps only, 1: size/dimension policy (default), 2: DMMA sweeps wherever possible
     int opt_gemm_staging;  // 1: cp.async ring (default), 2: TMA bulk-copy ring for aligned operands
+    long opt_superrow;     // DMMA sweeps: column chunks per super-row of the item order, 0 = sized for the L2 (default)
 };
 
 // the first kScratchScalars doubles of Context::scratch hold the scalar accumulators of the sweeps

@@ -123,6 +123,11 @@ extern "C" int cglb_set_option(cglb_context* c, const char* name, long value) {
         ctx->opt_dsweep = (int)value;
         return CGLB_OK;
     }
+    if (strcmp(name, "superrow") == 0) {
+        CGLB_CHECK_ARG(value >= 0, "superrow: chunks per super-row, 0 = automatic");
+        ctx->opt_superrow = value;
+        return CGLB_OK;
+    }
     if (strcmp(name, "gemm_staging") == 0) {
         CGLB_CHECK_ARG(value == 1 || value == 2, "gemm_staging: 1 (cp.async) or 2 (TMA)");
         ctx->opt_gemm_staging = (int)value;

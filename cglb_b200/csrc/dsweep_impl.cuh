@@ -41,6 +41,15 @@ __device__ __forceinline__ void dmma884c(double (&d)[2], double a, double b, dou
         : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
 
+// Work items and their order.  An item pairs the row block I (ROWS rows) with the column chunk c (DS_RPC x ROWS columns) for
+// every I < DS_RPC (c + 1): the columns at or after the row block.  Round 1 enumerated them chunk-major over ALL row blocks
+// (t = DS_RPC c (c + 1) / 2 + I); at n = 2M the rows a chunk pairs with (up to 192 MB of packed inputs) no longer fit the L2
+// and were re-read from DRAM for every chunk: 123 GB per launch (profiles/ncu_r02/dsweep_d11_n2M_raw.csv).  Now the row blocks
+// are grouped into SUPER-ROWS of R = DS_RPC Q blocks (Q = SweepArgs::sr_chunks chunks, ~48 MB of packed rows): within super-row s
+// the order is chunk-major over its own row blocks only, so its rows stay L2-resident while the column chunks stream by once.
+//   super-row s, local chunk k = c - s Q >= 0: row blocks s R .. min((s + 1) R, DS_RPC (c + 1)) - 1
+//   items per local chunk: DS_RPC (k + 1) for k < Q (triangular part), R for k >= Q (rectangular part)
+// cglb_b200/distributed.py: decode_strip_item is the host mirror (tests/test_host_logic.py: every pair exactly once).
 template <int ROWS>
 struct DCursor {
     static constexpr int DS_ROWS = ROWS, DS_CHUNK = DS_RPC * ROWS;
@@ -49,16 +58,38 @@ struct DCursor {
     long c0;        // first column of the first tile
     int tile, ntiles;
     bool valid;
+    __device__ __forceinline__ static void decode(long t, long n_chunks, long Q, long& I, long& c) {
+        const long R = DS_RPC * Q;
+        long s = 0;
+        for (;; ++s) {                                   // a handful of super-rows (4 at n = 2M)
+            const long nc = n_chunks - s * Q;            // chunks this super-row pairs with
+            const long kk = nc < Q ? nc : Q;
+            const long cnt = DS_RPC * kk * (kk + 1) / 2 + (nc > Q ? R * (nc - Q) : 0);
+            if (t < cnt || nc <= Q) break;               // (the last super-row takes whatever is left)
+            t -= cnt;
+        }
+        const long tri = DS_RPC * Q * (Q + 1) / 2;
+        long k, iloc;
+        if (t < tri) {
+            // chunk-major enumeration of {(i, k) : i < DS_RPC (k + 1)}: prefix(k) = DS_RPC k (k + 1) / 2
+            k = (long)((sqrt(1.0 + 8.0 * (double)t / DS_RPC) - 1.0) * 0.5);
+            while (DS_RPC * k * (k + 1) / 2 > t) --k;
+            while (DS_RPC * (k + 1) * (k + 2) / 2 <= t) ++k;
+            iloc = t - DS_RPC * k * (k + 1) / 2;
+        } else {
+            k = Q + (t - tri) / R;
+            iloc = (t - tri) % R;
+        }
+        c = s * Q + k;
+        I = s * R + iloc;
+    }
     __device__ __forceinline__ void load_item(const SweepArgs& a, long n_chunks) {
         for (;; tau += gridDim.x) {
             const long t = tau * a.nparts + a.part;
             valid = t < a.nitems;
             if (!valid) return;
-            // chunk-major enumeration of {(I, C) : I < DS_RPC (C + 1)}: prefix(C) = DS_RPC C (C + 1) / 2
-            long c = (long)((sqrt(1.0 + 8.0 * (double)t / DS_RPC) - 1.0) * 0.5);
-            while (DS_RPC * c * (c + 1) / 2 > t) --c;
-            while (DS_RPC * (c + 1) * (c + 2) / 2 <= t) ++c;
-            const long I = t - DS_RPC * c * (c + 1) / 2;
+            long I, c;
+            decode(t, n_chunks, a.sr_chunks, I, c);
             if (I >= a.nb_rows || c >= n_chunks) continue;
             r0 = I * DS_ROWS;
             long cbeg = c * DS_CHUNK;
@@ -77,6 +108,14 @@ struct DCursor {
         if (++tile == ntiles) { tau += gridDim.x; load_item(a, n_chunks); }
     }
 };
+
+// chunks per super-row: ~48 MB of packed rows (a chunk is DS_RPC x ROWS rows of dp doubles), overridden by the "superrow"
+// option (tests exercise several super-rows on small problems)
+static inline long dsweep_superrow_chunks(const Context* ctx, int dp, int rows) {
+    if (ctx->opt_superrow > 0) return ctx->opt_superrow;
+    const long q = (48L << 20) / ((long)DS_RPC * rows * dp * (long)sizeof(double));
+    return q < 1 ? 1 : q;
+}
 
 // WARPS warps x MT m-tiles (8 rows each) per warp; lane 0 of warp 0 also drives the TMA ring, as in the
 // register-resident sweep (a dedicated producer warp and 12 / 16-warp shapes were measured and are slower,
@@ -323,6 +362,7 @@ static int run_dsweep(Context* ctx, SweepArgs a, cudaStream_t st) {
     const long n_chunks = (a.ncols + CHUNK - 1) / CHUNK;
     a.nb_cols = n_chunks;
     a.nitems = DS_RPC * n_chunks * (n_chunks + 1) / 2;
+    a.sr_chunks = dsweep_superrow_chunks(ctx, DP, ROWS);
     auto kern = dmma_sweep_kernel<KIND, DP, WARPS, MT>;
     const size_t smem = dsweep_smem_bytes(DP, WARPS, CHUNK, ROWS);
     CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -588,6 +628,7 @@ static int run_dbwd(Context* ctx, SweepArgs a, cudaStream_t st) {
     const long n_chunks = (a.ncols + CHUNK - 1) / CHUNK;
     a.nb_cols = n_chunks;
     a.nitems = DS_RPC * n_chunks * (n_chunks + 1) / 2;
+    a.sr_chunks = dsweep_superrow_chunks(ctx, DP, ROWS);
     auto kern = dmma_bwd_kernel<KIND, D, WARPS, MT>;
     const size_t smem = (size_t)(DS_STAGES * kBJ * DP + DS_STAGES * 2 * kBJ + WARPS * CHUNK) * sizeof(double) + 2 * DS_STAGES * sizeof(uint64_t);
     CGLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -42,6 +42,7 @@ struct SweepArgs {
     long nrows, ncols;       // valid counts
     long nb_rows, nb_cols;   // number of BI blocks
     long nitems;             // total work items (global, before the part split)
+    long sr_chunks;          // DMMA sweeps: column chunks per super-row of the item order (dsweep_impl.cuh)
     const double* exp_tab;   // 64 doubles 2^(j/64) in global memory
     double variance;
     int part, nparts;

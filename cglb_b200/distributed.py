@@ -82,24 +82,53 @@ def symmetric_items(n: int, block: int):
             t += 1
 
 
-def strip_items(n: int, rows: int = 256, rows_per_chunk: int = 4, tile: int = 64):
-    """Enumeration of the DMMA sweeps' work items (DCursor in csrc/dsweep_impl.cuh): item t = rows_per_chunk *
-    C (C + 1) / 2 + I pairs the row block I (`rows` rows) with the column chunk C (`rows_per_chunk * rows`
-    columns), for every I < rows_per_chunk (C + 1) that exists; only the columns at or after the row block are
-    visited, in tiles of `tile` columns.  Yields (t, r0, r1, [(j0, j1, offdiag), ...]): tiles overlapping the row
-    block (offdiag False) are evaluated as ordered pairs and feed the row sums only, tiles beyond it feed the row
-    AND the column sums."""
+def decode_strip_item(t: int, n_chunks: int, rows_per_chunk: int, superrow_chunks: int):
+    """Item t of the DMMA sweeps -> (row block I, column chunk c): the host mirror of DCursor::decode in
+    csrc/dsweep_impl.cuh.  Row blocks are grouped into super-rows of R = rows_per_chunk * Q blocks (Q = superrow_chunks);
+    super-row s pairs its blocks with the chunks c >= s Q, chunk-major: rows_per_chunk (k + 1) items for the local chunk
+    k = c - s Q < Q (triangular part), R items for k >= Q."""
+    rpc, q = rows_per_chunk, superrow_chunks
+    r = rpc * q
+    s = 0
+    while True:
+        nc = n_chunks - s * q
+        kk = min(nc, q)
+        cnt = rpc * kk * (kk + 1) // 2 + (r * (nc - q) if nc > q else 0)
+        if t < cnt or nc <= q:
+            break
+        t -= cnt
+        s += 1
+    tri = rpc * q * (q + 1) // 2
+    if t < tri:
+        k = int(((1.0 + 8.0 * t / rpc) ** 0.5 - 1.0) * 0.5)
+        while rpc * k * (k + 1) // 2 > t:
+            k -= 1
+        while rpc * (k + 1) * (k + 2) // 2 <= t:
+            k += 1
+        iloc = t - rpc * k * (k + 1) // 2
+    else:
+        k = q + (t - tri) // r
+        iloc = (t - tri) % r
+    return s * r + iloc, s * q + k
+
+
+def strip_items(n: int, rows: int = 256, rows_per_chunk: int = 4, tile: int = 64, superrow_chunks: int = 1 << 30):
+    """Enumeration of the DMMA sweeps' work items (DCursor in csrc/dsweep_impl.cuh): item t pairs the row block I (`rows`
+    rows) with the column chunk C (`rows_per_chunk * rows` columns), for every I < rows_per_chunk (C + 1) that exists, in the
+    L2-blocked order of `decode_strip_item`; only the columns at or after the row block are visited, in tiles of `tile`
+    columns.  Yields (t, r0, r1, [(j0, j1, offdiag), ...]): tiles overlapping the row block (offdiag False) are evaluated as
+    ordered pairs and feed the row sums only, tiles beyond it feed the row AND the column sums."""
     chunk = rows_per_chunk * rows
     nb_rows = -(-n // rows)
     n_chunks = -(-n // chunk)
-    for c in range(n_chunks):
-        for i in range(rows_per_chunk * (c + 1)):
-            t = rows_per_chunk * c * (c + 1) // 2 + i
-            if i >= nb_rows:
-                continue
-            r0 = i * rows
-            cbeg, cend = max(c * chunk, r0), min((c + 1) * chunk, n)
-            if cbeg >= cend:
-                continue
-            tiles = [(j0, min(j0 + tile, cend), j0 >= r0 + rows) for j0 in range(cbeg, cend, tile)]
-            yield t, r0, min(r0 + rows, n), tiles
+    nitems = rows_per_chunk * n_chunks * (n_chunks + 1) // 2
+    for t in range(nitems):
+        i, c = decode_strip_item(t, n_chunks, rows_per_chunk, superrow_chunks)
+        if i >= nb_rows or c >= n_chunks:
+            continue
+        r0 = i * rows
+        cbeg, cend = max(c * chunk, r0), min((c + 1) * chunk, n)
+        if cbeg >= cend:
+            continue
+        tiles = [(j0, min(j0 + tile, cend), j0 >= r0 + rows) for j0 in range(cbeg, cend, tile)]
+        yield t, r0, min(r0 + rows, n), tiles

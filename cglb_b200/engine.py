@@ -91,10 +91,10 @@ class Engine:
 
     # ---- developer options ----------------------------------------------------------------------
     def set_option(self, name: str, value: int):
-        """cglb_set_option: "dsweep" 0 / 1 / 2, "gemm_staging" 1 (cp.async) / 2 (TMA)."""
+        """cglb_set_option: "dsweep" 0 / 1 / 2, "gemm_staging" 1 (cp.async) / 2 (TMA), "superrow" chunks per super-row (0 = auto)."""
         check(self.lib.cglb_set_option(self.ctx, name.encode(), int(value)), "cglb_set_option")
 
-    _ENV_OPTIONS = {"CGLB_DSWEEP": ("dsweep", 1), "CGLB_GEMM_STAGING": ("gemm_staging", 1)}
+    _ENV_OPTIONS = {"CGLB_DSWEEP": ("dsweep", 1), "CGLB_GEMM_STAGING": ("gemm_staging", 1), "CGLB_SUPERROW": ("superrow", 0)}
 
     def _sync_env_options(self):
         """The library reads its switches from the environment once (cglb_create); tests and tools flip them at run time, so

@@ -52,7 +52,8 @@ CGLB_API int cglb_create(cglb_context** ctx, int device);
 CGLB_API int cglb_destroy(cglb_context* ctx);
 /* Developer options of a context (not part of the reference's interface: they select between kernels that compute the
  * same thing).  "dsweep": 0 register-resident sweeps only, 1 the size / dimension policy (default), 2 DMMA sweeps wherever the
- * packed width allows; "gemm_staging": 1 cp.async operand ring (default), 2 TMA bulk-copy ring for 16-byte aligned operands.
+ * packed width allows; "gemm_staging": 1 cp.async operand ring (default), 2 TMA bulk-copy ring for 16-byte aligned operands;
+ * "superrow": column chunks per super-row of the DMMA sweeps' L2-blocked item order, 0 = sized for the L2 (default).
  * Initial values come from the environment variables CGLB_DSWEEP / CGLB_GEMM_STAGING, read once in cglb_create. */
 CGLB_API int cglb_set_option(cglb_context* ctx, const char* name, long value);
 

@@ -655,3 +655,31 @@ def test_dense_factorisations_with_tma_staging(eng):
         test_dense_factorisations(eng, 1024)
     finally:
         eng.set_option("gemm_staging", 1)
+
+
+@pytest.mark.parametrize("q", [1, 2, 3])
+def test_dmma_sweeps_with_several_super_rows(eng, monkeypatch, q):
+    """The L2-blocked item order of the DMMA sweeps (DCursor::decode): with `superrow` = q chunks a problem of 5000 rows spans
+    several super-rows (a chunk is 1024 rows); forward and backward sweeps against the oracle, and the 3-way work partition."""
+    monkeypatch.setenv("CGLB_DSWEEP", "2")
+    n, d, kind = 5000, 11, "matern32"
+    x, v, u, ls = _problem(n, d, seed=77)
+    dev = eng.device
+    xp = eng.pack(kind, x.to(dev), ls.to(dev), x.mean(0).to(dev))
+    try:
+        eng.set_option("superrow", q)
+        y = eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.3, 0.07)
+        ref = o.kernel_dense(kind, x, x, ls, torch.tensor(1.3, dtype=f64), block=1000) @ v + 0.07 * v
+        assert float((y.cpu() - ref).norm() / ref.norm()) <= MATVEC_TOL
+        parts = sum(eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.3, 0.07, part=p, nparts=3) for p in range(3))
+        assert float((parts - y).norm() / y.norm()) <= 1e-13
+        out = eng.zeros(d + 1)
+        eng.kmv_bwd_sym(kind, xp, n, d, u.to(dev), v.to(dev), 1.3, ls.to(dev), out)
+        eng.set_option("superrow", 0)
+        out0 = eng.zeros(d + 1)
+        eng.kmv_bwd_sym(kind, xp, n, d, u.to(dev), v.to(dev), 1.3, ls.to(dev), out0)
+        assert float((out - out0).abs().max() / out0.abs().max()) <= 1e-11
+        y0 = eng.kmv_sym(kind, xp, n, d, v.to(dev), 1.3, 0.07)
+        assert float((y - y0).norm() / y0.norm()) <= 1e-13
+    finally:
+        eng.set_option("superrow", 0)

@@ -111,7 +111,8 @@ def test_strip_items_cover_every_pair_once():
     import numpy as np
     from cglb_b200.distributed import Shard, strip_items
     rng = np.random.default_rng(0)
-    for n, rows, rpc, tile in [(700, 64, 4, 16), (1030, 128, 4, 64), (257, 256, 4, 64), (64, 16, 2, 8), (999, 32, 4, 8)]:
+    for n, rows, rpc, tile, q in [(700, 64, 4, 16, 1 << 30), (1030, 128, 4, 64, 1), (257, 256, 4, 64, 2), (64, 16, 2, 8, 1),
+                                  (999, 32, 4, 8, 3), (999, 32, 4, 8, 2), (2050, 16, 4, 16, 5), (1500, 16, 4, 16, 7)]:
         a = rng.standard_normal((n, n))
         K = a + a.T                                   # any symmetric matrix
         v = rng.standard_normal(n)
@@ -121,7 +122,7 @@ def test_strip_items_cover_every_pair_once():
             seen = set()
             for rank in range(world):
                 sh = Shard(rank, world)
-                for t, r0, r1, tiles in strip_items(n, rows, rpc, tile):
+                for t, r0, r1, tiles in strip_items(n, rows, rpc, tile, superrow_chunks=q):
                     if not sh.owns_item(t):
                         continue
                     assert t not in seen
@@ -133,4 +134,25 @@ def test_strip_items_cover_every_pair_once():
                             y[j0:j1] += blk.T @ v[r0:r1]
                         else:
                             assert j0 >= r0 and j1 <= r0 + rows      # inside the diagonal block: ordered pairs
-            assert np.allclose(y, ref, rtol=1e-12, atol=1e-10), (n, rows, world)
+            assert np.allclose(y, ref, rtol=1e-12, atol=1e-10), (n, rows, world, q)
+
+
+def test_strip_item_order_is_a_bijection_and_l2_blocked():
+    """decode_strip_item (mirror of DCursor::decode): every (row block, chunk) with I < rpc (c + 1) exactly once for any
+    super-row size; inside a super-row the items of one chunk are consecutive, and a super-row's row blocks are not
+    touched again once it is finished (the packed rows of one super-row are what has to stay in the L2)."""
+    from cglb_b200.distributed import decode_strip_item
+    for n_chunks, rpc, q in [(1, 4, 1), (7, 4, 1), (7, 4, 2), (7, 4, 3), (7, 4, 100), (13, 2, 5), (40, 4, 8), (1953, 4, 512)]:
+        nitems = rpc * n_chunks * (n_chunks + 1) // 2
+        step = 1 if nitems < 200000 else 997           # the headline shape is sampled
+        seen, last_sr = set(), -1
+        for t in range(0, nitems, step):
+            i, c = decode_strip_item(t, n_chunks, rpc, q)
+            assert 0 <= c < n_chunks and 0 <= i < rpc * (c + 1), (t, i, c)
+            assert (i, c) not in seen
+            seen.add((i, c))
+            sr = i // (rpc * q)
+            assert sr >= last_sr                           # super-rows are visited in order, never revisited
+            last_sr = sr
+        if step == 1:
+            assert len(seen) == nitems
