@@ -60,3 +60,14 @@ def test_committed_bench_lines_respect_the_roofline_convention():
         assert frac is None or 0.0 < frac <= 1.0, (path, frac)
         assert "achieved_nominal_n2" in j["roofline"]
         assert j["steps"] >= 1 and j["config"]["steps_requested"] >= j["steps"]
+
+
+def test_budget_estimate_ignores_the_cold_step_and_trusts_a_full_cycle():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.Budget.estimate([185.0]) == (185.0, bench.Budget.SAFETY)                 # only the cold step so far
+    assert bench.Budget.estimate([185.0, 75.0]) == (75.0, bench.Budget.SAFETY)            # CG from v = 0 is left out
+    est, safety = bench.Budget.estimate([185.0, 75.0, 83.0, 92.0])
+    assert est == 92.0 and safety == 1.05                                                  # a whole lengthscale cycle seen
+    est, safety = bench.Budget.estimate([185.0, 75.0, 83.0, 92.0, 75.0])
+    assert est == 92.0 and safety == 1.05
