@@ -31,6 +31,10 @@ CASES = [
     ("ragged_rbf_init", "rbf", 257, 2, 17, 1.0, 1.0, 1.0, 0.0, [1.0, 1.01], 14),
     ("wide_d_matern", "matern32", 300, 20, 32, 0.05, 1.0, 3.0, 0.0, [1.0], 15),
     ("song_like_wide", "matern32", 350, 90, 40, 0.05, 1.0, 4.7, 0.0, [1.0, 1.01], 17),
+    # M = 256 > the 128-wide panels of the blocked factorisations (round 2): the reference's own code pins the blocked
+    # potrf / TRSM / SYRK path through the bound, with a warm-started second evaluation
+    ("kin_like_m256", "rbf", 2000, 8, 256, 0.05, 1.0, 2.0, 0.0, [1.0, 1.01], 18),
+    ("house_like_m256", "matern32", 1500, 11, 256, 0.02, 1.0, 1.66, 0.0, [1.0, 1.01], 19),
     # restart branch of conjugate_gradient.py:70-75 exercised through LowerBoundCG(model, cg_opt=...)
     ("restart_path", "matern32", 400, 2, 6, 0.02, 1.5, 0.5, 0.0, [1.0], 16,
      dict(max_error=1e-3, restart_cg_iter=4, max_cg_iter=100)),
