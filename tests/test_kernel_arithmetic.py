@@ -2,6 +2,7 @@
 50-digit decimal arithmetic with the constants parsed from the CUDA source, so that the test follows the kernels:
   * exp: r = -s - n ln2/2^TB with n = rint(-s 2^TB/ln2), e^r by the short polynomial, 2^(n/2^TB) from a table;
   * sqrt: MUFU.RSQ64H seed (relative error <= 2^-20, measured) + one third-order correction."""
+import math
 import os
 import re
 from decimal import Decimal, getcontext
@@ -138,3 +139,31 @@ def test_kernel_map_end_to_end_in_emulated_fp64():
         assert err <= float(sq) * 2.6e-16 + 4e-16, (q, err)
         worst = max(worst, err / (float(sq) * 2.6e-16 + 4e-16))
     assert worst > 0.05          # the bound is not vacuous
+
+
+def test_exponent_insert_through_the_pre_biased_table():
+    """fast_exp_neg<10> (round 2): the 1024-entry table stores 2^(j/1024) with j << 10 subtracted from its high word
+    (context.cu), and ONE integer multiply-add  hi = n * 2^10 + hi(T'[n & 1023])  forms 2^(n/1024) for n = (n >> 10) 2^10 + j
+    without masking n.  Integer emulation of the two instructions against exact scaling, over the whole range the clamp allows
+    (s <= 693 -> n >= -1023999), and the claim that scaling by 2^k before or after the multiplication gives the same bits."""
+    import random
+    import struct
+    from decimal import Decimal, getcontext
+    getcontext().prec = 50
+    src = open(os.path.join(ROOT, "cglb_b200", "csrc", "context.cu")).read()
+    assert "bits -= (unsigned long long)j << 42;" in src                     # the table construction this test mirrors
+    table = [float(Decimal(2) ** (Decimal(j) / 1024)) for j in range(1024)]
+    biased = []
+    for j, t in enumerate(table):
+        bits = struct.unpack("<Q", struct.pack("<d", t))[0]
+        biased.append((bits - (j << 42)) & 0xFFFFFFFFFFFFFFFF)
+    rng = random.Random(0)
+    for n in [0, -1, -1023, -1024, -1025, -1023999, -512000] + [-rng.randrange(0, 1024000) for _ in range(2000)]:
+        j = n & 1023                                                         # two's complement: the low 10 bits
+        tb = biased[j]
+        hi = ((n * 1024) + (tb >> 32)) & 0xFFFFFFFF                          # mad.lo.s32 hi, n, 1024, hi(T')
+        val = struct.unpack("<d", struct.pack("<Q", (hi << 32) | (tb & 0xFFFFFFFF)))[0]
+        k = (n - j) // 1024                                                  # n >> 10 (arithmetic)
+        assert val == math.ldexp(table[j], k), (n, j, k)
+        x = 1.0 + rng.random() * 2.0 ** -11                                  # 1 + r p of the polynomial
+        assert math.ldexp(table[j], k) * x == math.ldexp(table[j] * x, k)    # scale first or last: same bits (no underflow)
