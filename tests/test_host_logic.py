@@ -156,3 +156,17 @@ def test_strip_item_order_is_a_bijection_and_l2_blocked():
             last_sr = sr
         if step == 1:
             assert len(seen) == nitems
+
+
+def test_fixed_order_accumulation_has_one_owner_thread_per_address():
+    """in the DMMA sweeps, address X of a CTA's private copy of y is added to by thread X % 256 only -- as a row
+    (row r0 + t belongs to thread t) and as a column (column c0 + col is flushed by thread col % 256) -- because row blocks and
+    the first column of every item are multiples of 256; program order of that one thread then fixes the summation order."""
+    from cglb_b200.distributed import strip_items
+    for n, q in ((5000, 1), (5000, 2), (70000, 16), (3000, 1 << 30)):
+        for t, r0, r1, tiles in strip_items(n, 256, 4, 64, superrow_chunks=q):
+            c0 = tiles[0][0]
+            assert r0 % 256 == 0 and c0 % 256 == 0, (t, r0, c0)
+            assert all(j0 % 64 == 0 for j0, _, _ in tiles)
+            # columns that receive column sums (tiles beyond the row block) never overlap the item's own rows
+            assert all(j0 >= r0 + 256 for j0, _, off in tiles if off)
