@@ -560,7 +560,7 @@ def test_cg_state_reuse_matches_the_recomputed_route(M, noise, max_error, expect
     assert abs(float(loss) - float(loss_r)) <= BOUND_TOL * abs(float(loss_r))
 
 
-@pytest.mark.parametrize("name", ["road_like_trained", "house_like_warmstart", "snelson_like_init"])
+@pytest.mark.parametrize("name", ["road_like_trained", "house_like_warmstart", "snelson_like_init", "kin_like_m256", "house_like_m256"])
 def test_predict_matches_reference_golden(name):
     g = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
     last = len(g["ls_mults"]) - 1

@@ -75,7 +75,7 @@ def test_fp32_golden_is_consistent_with_the_fp64_oracle(name):
         assert np.abs(gr.numpy() - ref).max() <= 1e-3 * np.abs(gr.numpy()).max() + 1e-6, gname
 
 
-@pytest.mark.parametrize("name", ["road_like_trained", "kin_like_rbf"])
+@pytest.mark.parametrize("name", ["road_like_trained", "kin_like_rbf", "kin_like_m256", "house_like_m256"])
 def test_predict_matches_reference_golden(name):
     g = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
     kind = str(g["kind"])
